@@ -1,0 +1,87 @@
+"""ctypes binding of libcfgpp_b200.so (the C-ABI boundary declared in include/cfgpp_b200.h).
+
+There is deliberately no fallback: if the library is absent or a call fails, this raises.
+PyTorch is used only as the owner of device memory and streams (raw pointers cross the boundary).
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+from pathlib import Path
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libcfgpp_b200.so"
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise NativeError(
+                f"{_LIB_PATH} not found — build it with `python -m cfgpp_b200.build` "
+                "(there is no CPU/eager fallback on the product path)")
+        _lib = ctypes.CDLL(str(_LIB_PATH))
+        _lib.cfgpp_last_error.restype = c_char_p
+        _lib.cfgpp_version.restype = c_int
+    return _lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        msg = load().cfgpp_last_error()
+        raise NativeError(f"cfgpp native call failed ({status}): {msg.decode() if msg else '?'}")
+
+
+def ptr(t: torch.Tensor | None) -> c_void_p:
+    if t is None:
+        return c_void_p(0)
+    assert t.is_cuda and t.is_contiguous(), "native ops take contiguous CUDA tensors"
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ------------------------------------------------------------------------------------------------
+# operator-level wrappers (one kernel launch each) — used by tests and micro-benchmarks
+# ------------------------------------------------------------------------------------------------
+def op_linear(a: torch.Tensor, w: torch.Tensor, bias=None, addend=None, add_rows_per_group: int = 1,
+              a2: torch.Tensor | None = None, geglu: bool = False, force_bn: int = 0) -> torch.Tensor:
+    """out = epilogue(cat([a, a2], -1) @ w.T); a [M,K1] fp16, w [N,K] fp16 (already packed for GEGLU)."""
+    lib = load()
+    M, K1 = a.shape
+    K = K1 + (a2.shape[1] if a2 is not None else 0)
+    N = w.shape[0]
+    assert w.shape[1] == K and a.dtype == torch.float16 and w.dtype == torch.float16
+    n_out = N // 2 if geglu else N
+    out = torch.empty((M, n_out), dtype=torch.float16, device=a.device)
+    check(lib.cfgpp_op_linear(ptr(a), c_int(a.stride(0)), ptr(a2), c_int(a2.stride(0) if a2 is not None else 0),
+                              c_int(K1), ptr(w), c_int(M), c_int(N), c_int(K), ptr(bias), ptr(addend),
+                              c_int(addend.stride(0) if addend is not None else 0), c_int(add_rows_per_group),
+                              ptr(out), c_int(n_out), c_int(1 if geglu else 0), c_int(force_bn), stream_ptr()))
+    return out
+
+
+def op_conv3x3(x_nhwc: torch.Tensor, w_packed: torch.Tensor, bias=None, addend=None,
+               add_rows_per_group: int = 1, force_bn: int = 0) -> torch.Tensor:
+    """x [B,H,W,Cin] fp16 NHWC, w_packed [Cout, 9*Cin] (tap-major), returns [B,H,W,Cout]."""
+    lib = load()
+    B, H, W, Cin = x_nhwc.shape
+    Cout = w_packed.shape[0]
+    assert w_packed.shape[1] == 9 * Cin
+    out = torch.empty((B, H, W, Cout), dtype=torch.float16, device=x_nhwc.device)
+    check(lib.cfgpp_op_conv3x3(ptr(x_nhwc), c_int(B), c_int(H), c_int(W), c_int(Cin), ptr(w_packed), c_int(Cout),
+                               ptr(bias), ptr(addend), c_int(addend.stride(0) if addend is not None else 0),
+                               c_int(add_rows_per_group), ptr(out), c_int(force_bn), stream_ptr()))
+    return out

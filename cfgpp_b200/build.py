@@ -1,0 +1,71 @@
+"""Build libcfgpp_b200.so (hand-written sm_100a CUDA behind a C ABI) in-tree with nvcc.
+
+    python -m cfgpp_b200.build [--force]
+
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot. There is no JIT and no CPU
+fallback: if the library is missing the product path raises.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+CSRC = ROOT / "csrc"
+OBJ = ROOT / "lib" / "obj"
+LIB = ROOT / "lib" / "libcfgpp_b200.so"
+INCLUDE = ROOT.parent / "include"
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+CFLAGS = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+          "--expt-relaxed-constexpr", "-I", str(INCLUDE), "-I", str(CSRC)]
+
+
+def _sources():
+    return sorted(CSRC.glob("*.cu"))
+
+
+def _deps_mtime() -> float:
+    hdrs = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list(INCLUDE.glob("*.h"))
+    return max((h.stat().st_mtime for h in hdrs), default=0.0)
+
+
+def _compile(src: Path, force: bool, hdr_mtime: float, verbose: bool) -> Path:
+    obj = OBJ / (src.stem + ".o")
+    if (not force and obj.exists() and obj.stat().st_mtime > src.stat().st_mtime
+            and obj.stat().st_mtime > hdr_mtime):
+        return obj
+    cmd = [NVCC, *ARCH, *CFLAGS, "-c", str(src), "-o", str(obj)]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")
+    if verbose:
+        sys.stderr.write(r.stderr)
+    return obj
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    OBJ.mkdir(parents=True, exist_ok=True)
+    srcs = _sources()
+    hdr_mtime = _deps_mtime()
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        objs = list(ex.map(lambda s: _compile(s, force, hdr_mtime, verbose), srcs))
+    newest = max(o.stat().st_mtime for o in objs)
+    if force or not LIB.exists() or LIB.stat().st_mtime < newest:
+        cmd = [NVCC, *ARCH, "-shared", "-o", str(LIB), *map(str, objs), "-lnccl_static_placeholder"]
+        cmd = [c for c in cmd if c != "-lnccl_static_placeholder"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(p)

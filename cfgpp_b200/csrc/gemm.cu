@@ -1,0 +1,373 @@
+// cfgpp_b200 — persistent, warp-specialised tcgen05 GEMM / implicit-GEMM conv3x3 kernel for sm_100a.
+// See gemm.cuh for the operator contract. Structure per CTA (256 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0 lane 0 : TMA producer  (A tile 128x64, B tile BNx64 per stage, 128B swizzle, mbarrier complete_tx)
+//   warp 1 lane 0 : MMA issuer    (tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16 x4 per stage)
+//   warp 2        : TMEM allocator
+//   warps 4..7    : epilogue      (tcgen05.ld 32x32b -> bias/addend/GEGLU -> fp16 global stores)
+// Pipelines: smem ring full/empty (TMA <-> MMA) and a 2-deep TMEM accumulator ring full/empty (MMA <-> epilogue),
+// so the epilogue of tile i overlaps the main loop of tile i+1.
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace cfgpp {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 256;
+constexpr int A_BYTES = BM * BK * 2;
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN >= 160 ? 5 : 6);
+  static constexpr int TMEM_COLS = (BN <= 64) ? 128 : (BN <= 128 ? 256 : 512);
+  static constexpr int ACC_STRIDE = TMEM_COLS / 2;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool GEGLU>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
+            const __grid_constant__ CUtensorMap map_b) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024B alignment (required by the 128B swizzle atoms) in the shared address space
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::STAGES;
+  uint64_t* tmem_full_bar = bars + 2 * C::STAGES;
+  uint64_t* tmem_empty_bar = bars + 2 * C::STAGES + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_a2);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int nkb = p.num_k_blocks;
+
+  if (warp_idx == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % p.num_m_blocks;
+        const int n_blk = tile / p.num_m_blocks;
+        const int m0 = m_blk * BM;
+        int img = 0, h0 = 0, w0 = 0;
+        if (p.conv) {
+          const int hw = p.H * p.W;
+          img = m0 / hw;
+          const int r = m0 - img * hw;
+          h0 = r / p.W;
+          w0 = r - h0 * p.W;
+        }
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          if (p.conv) {
+            const int tap = kb / p.cpb;
+            const int cb = kb - tap * p.cpb;
+            const int kh = tap / 3, kw = tap - kh * 3;
+            tma_load_4d(sa, &map_a, &full_bar[stage], cb * BK, w0 + kw - 1, h0 + kh - 1, img);
+          } else {
+            const int k0 = kb * BK;
+            if (k0 < p.k_split)
+              tma_load_2d(sa, &map_a, &full_bar[stage], k0, m0);
+            else
+              tma_load_2d(sa, &map_a2, &full_bar[stage], k0 - p.k_split, m0);
+          }
+          tma_load_2d(sb, &map_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = make_idesc_f16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * C::ACC_STRIDE;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+          const uint64_t a_desc = make_sdesc_sw128(a_addr, 1024, 0);
+          const uint64_t b_desc = make_sdesc_sw128(b_addr, 1024, 0);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (kb == nkb - 1) umma_commit(&tmem_full_bar[as]);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp_idx - 4;  // == warp_idx % 4: the TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int m_blk = tile % p.num_m_blocks;
+      const int n_blk = tile / p.num_m_blocks;
+      const int m = m_blk * BM + row;
+      mbar_wait(&tmem_full_bar[as], aph);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + as * C::ACC_STRIDE + lane_off;
+      const __half* add_row = nullptr;
+      if (p.addend != nullptr && m < p.M)
+        add_row = p.addend + static_cast<size_t>(p.add_rows_per_group > 1 ? m / p.add_rows_per_group : m) * p.ld_add;
+
+      if constexpr (!GEGLU) {
+        __half* out_row = p.out + static_cast<size_t>(m) * p.ldc;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_x32(t_base + c0, v);
+          tmem_ld_wait();
+          const int n0 = n_blk * BN + c0;
+          if (m < p.M && n0 < p.N) {
+            if (n0 + 32 <= p.N) {
+              uint32_t o[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
+                if (p.bias) {
+                  const __half2 b = *reinterpret_cast<const __half2*>(p.bias + n0 + 2 * j);
+                  x0 += __low2float(b);
+                  x1 += __high2float(b);
+                }
+                __half2 t = __floats2half2_rn(x0, x1);
+                if (add_row) {
+                  const __half2 a = *reinterpret_cast<const __half2*>(add_row + n0 + 2 * j);
+                  t = __floats2half2_rn(__low2float(t) + __low2float(a), __high2float(t) + __high2float(a));
+                }
+                o[j] = *reinterpret_cast<uint32_t*>(&t);
+              }
+              uint4* dst = reinterpret_cast<uint4*>(out_row + n0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            } else {
+              for (int j = 0; j < 32 && n0 + j < p.N; ++j) {
+                float x = __uint_as_float(v[j]);
+                if (p.bias) x += __half2float(p.bias[n0 + j]);
+                __half t = __float2half_rn(x);
+                if (add_row) t = __float2half_rn(__half2float(t) + __half2float(add_row[n0 + j]));
+                out_row[n0 + j] = t;
+              }
+            }
+          }
+        }
+      } else {
+        // value columns [0,128), gate columns [128,256) of this tile -> 128 output columns
+        __half* out_row = p.out + static_cast<size_t>(m) * p.ldc + n_blk * (BN / 2);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+          uint32_t va[32], vg[32];
+          tmem_ld_x32(t_base + c0, va);
+          tmem_ld_x32(t_base + BN / 2 + c0, vg);
+          tmem_ld_wait();
+          if (m < p.M) {
+            const int na = n_blk * BN + c0;  // packed-row index of the value half (bias is packed alike)
+            const int ng = na + BN / 2;
+            uint32_t o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float a0 = __uint_as_float(va[2 * j]), a1 = __uint_as_float(va[2 * j + 1]);
+              float g0 = __uint_as_float(vg[2 * j]), g1 = __uint_as_float(vg[2 * j + 1]);
+              if (p.bias) {
+                const __half2 ba = *reinterpret_cast<const __half2*>(p.bias + na + 2 * j);
+                const __half2 bg = *reinterpret_cast<const __half2*>(p.bias + ng + 2 * j);
+                a0 += __low2float(ba);
+                a1 += __high2float(ba);
+                g0 += __low2float(bg);
+                g1 += __high2float(bg);
+              }
+              const __half2 ah = __floats2half2_rn(a0, a1);
+              const __half2 gh = __floats2half2_rn(g0, g1);
+              const __half2 ge = __floats2half2_rn(gelu_erf_f(__low2float(gh)), gelu_erf_f(__high2float(gh)));
+              const __half2 r = __floats2half2_rn(__low2float(ah) * __low2float(ge), __high2float(ah) * __high2float(ge));
+              o[j] = *reinterpret_cast<const uint32_t*>(&r);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(out_row + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BN, bool GEGLU>
+void launch(const GemmOp& op, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    CFGPP_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          C::SMEM_BYTES));
+    configured = true;
+  }
+  gemm_kernel<BN, GEGLU><<<op.grid, kThreads, C::SMEM_BYTES, stream>>>(op.p, op.map_a, op.map_a2, op.map_b);
+  CFGPP_CHECK_CUDA(cudaGetLastError());
+}
+
+// tile-width heuristic: fewest (waves x per-tile cost) over the allowed widths
+int choose_bn(int M, int N, bool geglu) {
+  if (geglu) return 256;
+  const int sms = num_sms();
+  const int mb = (M + BM - 1) / BM;
+  const int cand[4] = {256, 160, 128, 64};
+  int best = 128;
+  double best_cost = 1e30;
+  for (int bn : cand) {
+    if (bn == 160 && N % 160 != 0) continue;
+    const int nb = (N + bn - 1) / bn;
+    const long tiles = static_cast<long>(mb) * nb;
+    const long waves = (tiles + sms - 1) / sms;
+    // per-tile cost ~ MMA time (∝ bn) with a floor for narrow tiles (smem-bandwidth / issue bound)
+    const double tile_cost = (bn < 128 ? 128 * 1.15 : bn) + 24.0;
+    const double cost = waves * tile_cost;
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+void finish_op(GemmOp& op, const __half* w, int force_bn) {
+  GemmParams& p = op.p;
+  op.bn = force_bn ? force_bn : choose_bn(p.M, p.N, p.geglu != 0);
+  CFGPP_REQUIRE(op.bn == 64 || op.bn == 128 || op.bn == 160 || op.bn == 256, "unsupported BN");
+  if (p.geglu) CFGPP_REQUIRE(op.bn == 256 && p.N % 256 == 0, "GEGLU needs N % 256 == 0");
+  p.num_m_blocks = (p.M + BM - 1) / BM;
+  p.num_n_blocks = (p.N + op.bn - 1) / op.bn;
+  op.map_b = make_tmap_2d(w, p.N, p.K, p.K, op.bn);
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  op.grid = tiles < num_sms() ? tiles : num_sms();
+}
+
+}  // namespace
+
+GemmOp make_linear_op(const __half* a, int lda, const __half* a2, int lda2, int k_split, const __half* w, int M,
+                      int N, int K, const __half* bias, const __half* addend, int ld_add, int add_rows_per_group,
+                      __half* out, int ldc, bool geglu, int force_bn) {
+  GemmOp op{};
+  GemmParams& p = op.p;
+  CFGPP_REQUIRE(K % BK == 0, "linear K must be a multiple of 64");
+  CFGPP_REQUIRE(N % 8 == 0 && ldc % 8 == 0, "N and ldc must be multiples of 8");
+  p.M = M; p.N = N; p.K = K;
+  p.num_k_blocks = K / BK;
+  p.conv = 0; p.cpb = 1; p.H = p.W = 1;
+  p.k_split = a2 ? k_split : K;
+  if (a2) CFGPP_REQUIRE(k_split % BK == 0 && k_split > 0 && k_split < K, "k_split must be a multiple of 64");
+  p.bias = bias; p.addend = addend; p.ld_add = ld_add;
+  p.add_rows_per_group = add_rows_per_group < 1 ? 1 : add_rows_per_group;
+  p.out = out; p.ldc = ldc; p.geglu = geglu ? 1 : 0;
+  op.map_a = make_tmap_2d(a, M, a2 ? k_split : K, lda, BM);
+  op.map_a2 = a2 ? make_tmap_2d(a2, M, K - k_split, lda2, BM) : op.map_a;
+  finish_op(op, w, force_bn);
+  return op;
+}
+
+GemmOp make_conv3x3_op(const __half* x, int B, int H, int W, int Cin, const __half* w, int Cout, const __half* bias,
+                       const __half* addend, int ld_add, int add_rows_per_group, __half* out, int force_bn) {
+  GemmOp op{};
+  GemmParams& p = op.p;
+  CFGPP_REQUIRE(Cin % BK == 0, "conv3x3 Cin must be a multiple of 64");
+  CFGPP_REQUIRE(Cout % 8 == 0, "conv3x3 Cout must be a multiple of 8");
+  CFGPP_REQUIRE((W & (W - 1)) == 0 && (H & (H - 1)) == 0 && W <= 128, "conv3x3 needs power-of-two H, W with W <= 128");
+  const int Wt = W;
+  const int Ht = (BM / Wt) < H ? (BM / Wt) : H;
+  const int Nt = BM / (Wt * Ht);
+  p.M = B * H * W; p.N = Cout; p.K = 9 * Cin;
+  p.num_k_blocks = 9 * (Cin / BK);
+  p.conv = 1; p.cpb = Cin / BK; p.H = H; p.W = W;
+  p.k_split = p.K;
+  p.bias = bias; p.addend = addend; p.ld_add = ld_add;
+  p.add_rows_per_group = add_rows_per_group < 1 ? 1 : add_rows_per_group;
+  p.out = out; p.ldc = Cout; p.geglu = 0;
+  uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+  uint32_t box[4] = {64, (uint32_t)Wt, (uint32_t)Ht, (uint32_t)Nt};
+  op.map_a = make_tmap_f16(x, 4, dims, strides, box);
+  op.map_a2 = op.map_a;
+  finish_op(op, w, force_bn);
+  return op;
+}
+
+void run_gemm_op(const GemmOp& op, cudaStream_t stream) {
+  if (op.p.geglu) return launch<256, true>(op, stream);
+  switch (op.bn) {
+    case 64: return launch<64, false>(op, stream);
+    case 128: return launch<128, false>(op, stream);
+    case 160: return launch<160, false>(op, stream);
+    case 256: return launch<256, false>(op, stream);
+    default: throw Error(-1, "bad BN");
+  }
+}
+
+}  // namespace cfgpp

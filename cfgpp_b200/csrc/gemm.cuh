@@ -1,0 +1,60 @@
+// cfgpp_b200 — tcgen05 GEMM / implicit-GEMM conv3x3 operator (host interface).
+//
+//   out[M,N] = epilogue( A[M,K] * B[N,K]^T )         fp16 in, fp32 accumulate in TMEM, fp16 out
+//
+// A is the activation in NHWC (= tokens x channels, K contiguous); B is the packed weight (N x K, K contiguous).
+// Modes:
+//   linear     : A through a 2D tensor map; optional second A source for K >= k_split (channel concat of
+//                two tensors, used by the 1x1 shortcut conv on torch.cat([h, skip]) in up-blocks).
+//   conv3x3    : stride 1, pad 1. A through a 4D tensor map (C, W, H, B); the K loop walks the 9 taps and
+//                issues shifted TMA box loads whose out-of-bounds pixels are zero-filled by the hardware
+//                (= the padding). Weight packed as [Cout][tap][Cin].
+// Epilogue (mirrors the rounding points of the reference's fp16 autocast graph):
+//   t = fp16(acc + bias[n]);  out = addend ? fp16(float(t) + float(addend)) : t
+//   addend is either a full residual [M, ld_add] or a per-sample row broadcast [M / add_rows_per_group][ld_add]
+//   (the ResnetBlock2D time-embedding add).
+//   GEGLU variant: weight rows interleaved per 256-wide tile as 128 'value' rows + 128 'gate' rows;
+//   out[m, j] = fp16( fp16(a) * fp16(gelu_erf(fp16(g))) ), N_out = N / 2.
+#pragma once
+#include "host.h"
+
+namespace cfgpp {
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_blocks, num_n_blocks, num_k_blocks;
+  int conv;     // 0 linear, 1 conv3x3
+  int cpb;      // conv: channel blocks (Cin / 64) per tap
+  int H, W;     // conv: spatial size
+  int k_split;  // linear: first K index served by the second A map (== K when single-source)
+  const __half* bias;
+  const __half* addend;
+  int ld_add;
+  int add_rows_per_group;  // 1: full residual; >1: row m uses addend row (m / add_rows_per_group)
+  __half* out;
+  int ldc;
+  int geglu;
+};
+
+struct GemmOp {
+  CUtensorMap map_a, map_a2, map_b;
+  GemmParams p;
+  int bn;
+  int grid;
+  // FLOP accounting (algorithmic): 2*M*N*K
+  double flops() const { return 2.0 * p.M * (double)p.N * p.K; }
+};
+
+// Linear: A [M,K] with leading dim lda (elements). Optional second source a2 (cols k_split..K) with lda2.
+GemmOp make_linear_op(const __half* a, int lda, const __half* a2, int lda2, int k_split, const __half* w, int M,
+                      int N, int K, const __half* bias, const __half* addend, int ld_add, int add_rows_per_group,
+                      __half* out, int ldc, bool geglu, int force_bn = 0);
+
+// Conv3x3 stride 1 pad 1 on NHWC input x [B,H,W,Cin], weight [Cout][9][Cin], out NHWC [B,H,W,Cout].
+GemmOp make_conv3x3_op(const __half* x, int B, int H, int W, int Cin, const __half* w, int Cout,
+                       const __half* bias, const __half* addend, int ld_add, int add_rows_per_group, __half* out,
+                       int force_bn = 0);
+
+void run_gemm_op(const GemmOp& op, cudaStream_t stream);
+
+}  // namespace cfgpp

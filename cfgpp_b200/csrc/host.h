@@ -1,0 +1,44 @@
+// cfgpp_b200 — host-side helpers: error handling, TMA tensor-map encoding (driver entry point fetched at
+// run time so the library does not link libcuda), device properties.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+namespace cfgpp {
+
+struct Error : public std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define CFGPP_CHECK_CUDA(expr)                                                                     \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      throw ::cfgpp::Error(-2, std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " + \
+                                   __FILE__ + ":" + std::to_string(__LINE__));                     \
+  } while (0)
+
+#define CFGPP_REQUIRE(cond, msg)                                                                          \
+  do {                                                                                                    \
+    if (!(cond))                                                                                          \
+      throw ::cfgpp::Error(-1, std::string("requirement failed: ") + #cond + " — " + (msg) + " at " +     \
+                                   __FILE__ + ":" + std::to_string(__LINE__));                            \
+  } while (0)
+
+int num_sms();
+
+// Generic fp16 tiled tensor map, 128B swizzle. dims/strides innermost first; strides[i] is the byte
+// stride of dim i+1 (dim 0 is contiguous). OOB elements are zero-filled by the hardware.
+CUtensorMap make_tmap_f16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                          const uint32_t* box);
+
+// 2D row-major [rows][cols] fp16 with leading dimension ld (elements); box = (64 cols, box_rows).
+CUtensorMap make_tmap_2d(const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+
+}  // namespace cfgpp
