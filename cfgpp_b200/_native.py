@@ -85,3 +85,50 @@ def op_conv3x3(x_nhwc: torch.Tensor, w_packed: torch.Tensor, bias=None, addend=N
                                ptr(bias), ptr(addend), c_int(addend.stride(0) if addend is not None else 0),
                                c_int(add_rows_per_group), ptr(out), c_int(force_bn), stream_ptr()))
     return out
+
+
+def op_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int) -> torch.Tensor:
+    """q [B,Nq,H*64], k/v [B,Nkv,H*64] fp16 (views with a row stride are fine) -> [B,Nq,H*64]."""
+    lib = load()
+    B, Nq, C = q.shape
+    Nkv = k.shape[1]
+    out = torch.empty((B, Nq, C), dtype=torch.float16, device=q.device)
+    for t in (q, k, v):
+        assert t.is_cuda and t.stride(2) == 1 and t.stride(0) == t.shape[1] * t.stride(1)
+    check(lib.cfgpp_op_attention(c_void_p(q.data_ptr()), c_int(q.stride(1)), c_void_p(k.data_ptr()), c_int(k.stride(1)),
+                                 c_void_p(v.data_ptr()), c_int(v.stride(1)), ptr(out), c_int(C), c_int(B),
+                                 c_int(heads), c_int(Nq), c_int(Nkv), stream_ptr()))
+    return out
+
+
+def op_groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool,
+                 x2: torch.Tensor | None = None) -> torch.Tensor:
+    """x1 [B,HW,C1] (+ x2 [B,HW,C2]) NHWC fp16 -> GroupNorm(32) over the channel concat, optional SiLU."""
+    lib = load()
+    B, HW, C1 = x1.shape
+    C2 = x2.shape[2] if x2 is not None else 0
+    out = torch.empty((B, HW, C1 + C2), dtype=torch.float16, device=x1.device)
+    check(lib.cfgpp_op_groupnorm(ptr(x1), c_int(C1), ptr(x2), c_int(C2), c_int(B), c_int(HW), ptr(gamma), ptr(beta),
+                                 c_float(eps), c_int(1 if silu else 0), ptr(out), stream_ptr()))
+    return out
+
+
+def op_layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    lib = load()
+    M, C = x.shape
+    out = torch.empty_like(x)
+    check(lib.cfgpp_op_layernorm(ptr(x), c_int(M), c_int(C), ptr(gamma), ptr(beta), c_float(eps), ptr(out),
+                                 stream_ptr()))
+    return out
+
+
+def op_cfgpp_step(eps_uc: torch.Tensor, eps_c: torch.Tensor, method: int, coef, z: torch.Tensor,
+                  aux: torch.Tensor | None = None, want_z0t: bool = True):
+    """In-place CFG++ update of z (fp32 or fp16 state) from given eps; returns z0t (or None)."""
+    from ctypes import byref
+    lib = load()
+    z0t = torch.empty_like(z) if want_z0t else None
+    code = 0 if z.dtype == torch.float16 else 1
+    check(lib.cfgpp_op_cfgpp_step(ptr(eps_uc), ptr(eps_c), c_int(z.numel()), c_int(method), c_int(code), byref(coef),
+                                  ptr(z), ptr(aux), ptr(z0t), stream_ptr()))
+    return z0t

@@ -2,7 +2,10 @@
 // Declared in include/cfgpp_b200.h. No C++ exception crosses the boundary: every entry point returns an int
 // status (0 = OK) and records a message retrievable with cfgpp_last_error().
 #include "capi_util.h"
+#include "attention.cuh"
 #include "gemm.cuh"
+#include "ops.cuh"
+#include "../../include/cfgpp_b200.h"
 
 using namespace cfgpp;
 
@@ -26,6 +29,62 @@ CFGPP_API int cfgpp_op_conv3x3(const void* x, int B, int H, int W, int Cin, cons
     GemmOp op = make_conv3x3_op((const __half*)x, B, H, W, Cin, (const __half*)w, Cout, (const __half*)bias,
                                 (const __half*)addend, ld_add, add_rows_per_group, (__half*)out, force_bn);
     run_gemm_op(op, (cudaStream_t)stream);
+  });
+}
+
+CFGPP_API int cfgpp_op_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out,
+                                 int ldo, int B, int H, int Nq, int Nkv, void* stream) {
+  return guarded([&] {
+    AttnOp op = make_attn_op((const __half*)q, ldq, (const __half*)k, ldk, (const __half*)v, ldv, (__half*)out, ldo,
+                             B, H, Nq, Nkv);
+    run_attn_op(op, (cudaStream_t)stream);
+  });
+}
+
+CFGPP_API int cfgpp_op_groupnorm(const void* x1, int C1, const void* x2, int C2, int B, int HW, const void* gamma,
+                                 const void* beta, float eps, int silu, void* out, void* stream) {
+  return guarded([&] {
+    float* partial = nullptr;
+    CFGPP_CHECK_CUDA(cudaMalloc(&partial, gn_partial_floats(B, HW) * sizeof(float)));
+    try {
+      run_groupnorm((const __half*)x1, C1, (const __half*)x2, C2, B, HW, (const __half*)gamma, (const __half*)beta,
+                    eps, silu != 0, partial, (__half*)out, (cudaStream_t)stream);
+    } catch (...) {
+      cudaFree(partial);
+      throw;
+    }
+    CFGPP_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));  // test-only entry point: scratch freed below
+    cudaFree(partial);
+  });
+}
+
+CFGPP_API int cfgpp_op_layernorm(const void* x, int M, int C, const void* gamma, const void* beta, float eps,
+                                 void* out, void* stream) {
+  return guarded([&] {
+    run_layernorm((const __half*)x, M, C, (const __half*)gamma, (const __half*)beta, eps, (__half*)out,
+                  (cudaStream_t)stream);
+  });
+}
+
+CFGPP_API int cfgpp_op_cfgpp_step(const void* eps_uc, const void* eps_c, int n, int method, int state_dtype,
+                                  const cfgpp_step_coef* coef_host, void* z, void* aux, void* z0t_out, void* stream) {
+  return guarded([&] {
+    static_assert(sizeof(cfgpp_step_coef) == sizeof(StepCoef), "ABI struct mismatch");
+    StepCoef* coef_dev = nullptr;
+    CFGPP_CHECK_CUDA(cudaMalloc(&coef_dev, sizeof(StepCoef)));
+    cudaError_t e = cudaMemcpy(coef_dev, coef_host, sizeof(StepCoef), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+      try {
+        run_step_only((const __half*)eps_uc, (const __half*)eps_c, n, method | (state_dtype == CFGPP_F16 ? 0x100 : 0),
+                      coef_dev, z, aux, z0t_out, (cudaStream_t)stream);
+      } catch (...) {
+        cudaFree(coef_dev);
+        throw;
+      }
+      e = cudaStreamSynchronize((cudaStream_t)stream);  // test-only entry point
+    }
+    cudaFree(coef_dev);
+    CFGPP_CHECK_CUDA(e);
   });
 }
 

@@ -180,6 +180,12 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N, ui
 CFGPP_DEVICE float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 CFGPP_DEVICE float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+CFGPP_DEVICE float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 CFGPP_DEVICE uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);

@@ -11,6 +11,8 @@
 
 namespace cfgpp {
 
+void gemm_configure();
+
 namespace {
 
 constexpr int BM = 128;
@@ -262,14 +264,15 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
 }
 
 template <int BN, bool GEGLU>
+void configure_one() {
+  CFGPP_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg<BN>::SMEM_BYTES));
+}
+
+template <int BN, bool GEGLU>
 void launch(const GemmOp& op, cudaStream_t stream) {
   using C = Cfg<BN>;
-  static bool configured = false;
-  if (!configured) {
-    CFGPP_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          C::SMEM_BYTES));
-    configured = true;
-  }
+  gemm_configure();
   gemm_kernel<BN, GEGLU><<<op.grid, kThreads, C::SMEM_BYTES, stream>>>(op.p, op.map_a, op.map_a2, op.map_b);
   CFGPP_CHECK_CUDA(cudaGetLastError());
 }
@@ -311,6 +314,18 @@ void finish_op(GemmOp& op, const __half* w, int force_bn) {
 }
 
 }  // namespace
+
+// opt every instantiation into its dynamic shared memory size once per process (not capturable: done eagerly)
+void gemm_configure() {
+  static bool done = false;
+  if (done) return;
+  configure_one<64, false>();
+  configure_one<128, false>();
+  configure_one<160, false>();
+  configure_one<256, false>();
+  configure_one<256, true>();
+  done = true;
+}
 
 GemmOp make_linear_op(const __half* a, int lda, const __half* a2, int lda2, int k_split, const __half* w, int M,
                       int N, int K, const __half* bias, const __half* addend, int ld_add, int add_rows_per_group,

@@ -1,0 +1,154 @@
+"""NativeUNet — Python owner of one `cfgpp_handle` (one per process and GPU).
+
+Replaces `pipe.unet` of the reference (latent_diffusion.py:67, latent_sdxl.py:50,391) plus the arithmetic between
+UNet calls: everything below goes through the C ABI of libcfgpp_b200.so into hand-written sm_100a kernels.
+PyTorch only owns the tensors and the stream. There is no eager / CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, byref, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _native as nv
+from .config import UNetConfig, to_desc
+from .schedule import F16, F32, StepStateC, to_c_array
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float16:
+        return F16
+    if t.dtype == torch.float32:
+        return F32
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+class NativeUNet:
+    def __init__(self, cfg: UNetConfig, state_dict: Dict[str, torch.Tensor], device="cuda:0"):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise nv.NativeError("the cfgpp_b200 backend runs on CUDA (sm_100a) only; use the oracle for CPU runs")
+        self.lib = nv.load()
+        self._h = c_void_p()
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", idx)
+        desc = to_desc(cfg)
+        with torch.cuda.device(self.device):
+            nv.check(self.lib.cfgpp_create(byref(desc), c_int(idx), byref(self._h)))
+            st = nv.stream_ptr()
+            for key, w in state_dict.items():
+                wd = w.detach().to(self.device).contiguous()
+                shape = (c_int64 * wd.dim())(*wd.shape)
+                nv.check(self.lib.cfgpp_load_weight(self._h, key.encode(), nv.ptr(wd), shape, c_int(wd.dim()),
+                                                    c_int(_dtype_code(wd)), st))
+                del wd
+            torch.cuda.synchronize(self.device)
+            nv.check(self.lib.cfgpp_finalize_weights(self._h, st))
+        self.batch = 0
+        self.latent_hw = (0, 0)
+        self._nsteps = 0
+        self._state_dtype = torch.float32
+
+    def close(self):
+        if self._h:
+            self.lib.cfgpp_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    # ---- plan ------------------------------------------------------------------------------------------------
+    def prepare(self, batch: int, h_lat: int, w_lat: int):
+        if (batch, (h_lat, w_lat)) == (self.batch, self.latent_hw):
+            return
+        with torch.cuda.device(self.device):
+            nv.check(self.lib.cfgpp_prepare(self._h, c_int(batch), c_int(h_lat), c_int(w_lat)))
+        self.batch, self.latent_hw = batch, (h_lat, w_lat)
+        self._nsteps = 0
+
+    @property
+    def workspace_bytes(self) -> int:
+        n = c_size_t()
+        nv.check(self.lib.cfgpp_workspace_bytes(self._h, byref(n)))
+        return n.value
+
+    @property
+    def forward_flops(self) -> float:
+        f = c_double()
+        nv.check(self.lib.cfgpp_forward_flops(self._h, byref(f)))
+        return f.value
+
+    @property
+    def launches_per_step(self) -> int:
+        n = c_int()
+        nv.check(self.lib.cfgpp_launches_per_step(self._h, byref(n)))
+        return n.value
+
+    # ---- conditioning ----------------------------------------------------------------------------------------
+    def set_prompt(self, ctx: torch.Tensor, pooled: Optional[torch.Tensor] = None,
+                   time_ids: Optional[torch.Tensor] = None):
+        """ctx = cat([uc, c]) (2*batch, n_ctx, D); pooled (rows, pooled_dim), time_ids (rows, 6), rows in
+        {batch, 2*batch} (latent_sdxl.py:249-257)."""
+        nb = 2 * self.batch
+        assert ctx.shape[0] == nb, f"ctx must have 2*batch={nb} rows"
+        ctx = ctx.to(self.device, torch.float16).contiguous()
+        add_rows = 0
+        if pooled is not None:
+            pooled = pooled.to(self.device, torch.float16).contiguous()
+            time_ids = time_ids.to(self.device, torch.float32).contiguous()
+            add_rows = pooled.shape[0]
+            assert time_ids.shape == (add_rows, 6)
+        with torch.cuda.device(self.device):
+            nv.check(self.lib.cfgpp_set_prompt(self._h, nv.ptr(ctx), c_int(ctx.shape[1]), nv.ptr(pooled),
+                                               ctypes.cast(nv.ptr(time_ids), POINTER(c_float)), c_int(add_rows),
+                                               nv.stream_ptr()))
+
+    # ---- un-fused seam: predict_noise ------------------------------------------------------------------------
+    def predict_noise(self, z: torch.Tensor, t: float, in_scale: float = 1.0):
+        z = z.to(self.device).contiguous()
+        eps_uc = torch.empty(z.shape, dtype=torch.float16, device=self.device)
+        eps_c = torch.empty_like(eps_uc)
+        with torch.cuda.device(self.device):
+            nv.check(self.lib.cfgpp_unet_forward(self._h, nv.ptr(z), c_int(_dtype_code(z)), c_float(float(t)),
+                                                 c_float(float(in_scale)), nv.ptr(eps_uc), nv.ptr(eps_c),
+                                                 nv.stream_ptr()))
+        return eps_uc, eps_c
+
+    # ---- fused trajectory ------------------------------------------------------------------------------------
+    def set_schedule(self, method: int, state_dtype: torch.dtype, steps: Sequence[StepStateC]):
+        arr = to_c_array(list(steps))
+        code = F16 if state_dtype == torch.float16 else F32
+        with torch.cuda.device(self.device):
+            nv.check(self.lib.cfgpp_set_schedule(self._h, c_int(method), c_int(code), arr, c_int(len(steps)),
+                                                 nv.stream_ptr()))
+            torch.cuda.current_stream().synchronize()  # the host table is staged; keep `arr` alive until then
+        self._nsteps = len(steps)
+        self._state_dtype = state_dtype
+
+    def set_state(self, z: torch.Tensor):
+        z = z.to(self.device, self._state_dtype).contiguous()
+        with torch.cuda.device(self.device):
+            nv.check(self.lib.cfgpp_set_state(self._h, nv.ptr(z), c_int(_dtype_code(z)), nv.stream_ptr()))
+
+    def run_steps(self, first: int = 0, n: Optional[int] = None):
+        n = self._nsteps - first if n is None else n
+        with torch.cuda.device(self.device):
+            nv.check(self.lib.cfgpp_run_steps(self._h, c_int(first), c_int(n), nv.stream_ptr()))
+
+    def get_state(self, which: int = 0) -> torch.Tensor:
+        h, w = self.latent_hw
+        out = torch.empty((self.batch, 4, h, w), dtype=self._state_dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            nv.check(self.lib.cfgpp_get_state(self._h, c_int(which), nv.ptr(out), nv.stream_ptr()))
+        return out
+
+    def apply_step(self, step: int, eps_uc: torch.Tensor, eps_c: torch.Tensor):
+        with torch.cuda.device(self.device):
+            nv.check(self.lib.cfgpp_apply_step(self._h, c_int(step), nv.ptr(eps_uc.contiguous()),
+                                               nv.ptr(eps_c.contiguous()), nv.stream_ptr()))

@@ -1,0 +1,149 @@
+"""Scheduler tables and per-step scalar coefficients of the CFG++ solvers (product side).
+
+The reference only uses diffusers schedulers as a *table source* (`scheduler.step()` is never called):
+  StableDiffusion.__init__   latent_diffusion.py:69-80      SDXL.__init__  latent_sdxl.py:56-67
+  SDXLLightning.__init__     latent_sdxl.py:407-418
+and computes every per-step scalar with fp32 torch CPU ops inside the loops
+  ddim_cfg++ (SD1.5)  latent_diffusion.py:655-656   ddim_cfg++ (SDXL)  latent_sdxl.py:731-734
+  inversion           latent_diffusion.py:899-900   dpm++_2m_cfgpp     latent_sdxl.py:877-879, 892-918.
+Here the same fp32 torch CPU ops are evaluated once per trajectory into a table (`cfgpp_step_state[]`) that the
+fused step kernel indexes on the device — removing the 2–3 host syncs per step the reference incurs
+(`alphas_cumprod[t]` indexes a CPU tensor with a CUDA scalar; `t >= 0`).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import List
+
+import numpy as np
+import torch
+
+NUM_TRAIN_TIMESTEPS = 1000
+
+STEP_NONE, STEP_DDIM_CFGPP, STEP_DDIM_INV_CFGPP, STEP_DPMPP2M_CFGPP = 0, 1, 2, 3
+F16, F32 = 0, 1
+
+
+class StepCoefC(ctypes.Structure):
+    _fields_ = [("lambda_", ctypes.c_float), ("c0", ctypes.c_float), ("c1", ctypes.c_float), ("c2", ctypes.c_float),
+                ("c3", ctypes.c_float), ("d0", ctypes.c_float), ("d1", ctypes.c_float), ("d2", ctypes.c_float),
+                ("d3", ctypes.c_float), ("second_order", ctypes.c_int)]
+
+
+class StepStateC(ctypes.Structure):
+    _fields_ = [("t", ctypes.c_float), ("in_scale", ctypes.c_float), ("coef", StepCoefC)]
+
+
+def alphas_cumprod_table() -> torch.Tensor:
+    betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, NUM_TRAIN_TIMESTEPS, dtype=torch.float32) ** 2
+    return torch.cumprod(1.0 - betas, dim=0)
+
+
+def ddim_leading_timesteps(n: int, steps_offset: int = 1) -> torch.Tensor:
+    ratio = NUM_TRAIN_TIMESTEPS // n
+    ts = (np.arange(0, n) * ratio).round()[::-1].copy().astype(np.int64)
+    return torch.from_numpy(ts + steps_offset)
+
+
+def euler_trailing_timesteps(n: int) -> torch.Tensor:
+    ts = np.round(np.arange(NUM_TRAIN_TIMESTEPS, 0, -NUM_TRAIN_TIMESTEPS / n)) - 1
+    return torch.from_numpy(ts.astype(np.float32))
+
+
+@dataclass
+class Schedule:
+    """State the reference keeps on `self` / `self.scheduler` after __init__."""
+    total_alphas: torch.Tensor
+    sigmas: torch.Tensor
+    log_sigmas: torch.Tensor
+    timesteps: torch.Tensor
+    skip: int
+    alphas_cumprod: torch.Tensor       # shifted: cat([1.0], abar) — index t == original t-1
+    final_alpha_cumprod: torch.Tensor
+
+    @staticmethod
+    def make(num_sampling: int, kind: str = "ddim") -> "Schedule":
+        abar = alphas_cumprod_table()
+        sig = (1 - abar).sqrt() / abar.sqrt()
+        ts = ddim_leading_timesteps(num_sampling) if kind == "ddim" else euler_trailing_timesteps(num_sampling)
+        return Schedule(abar.clone(), sig, sig.log(), ts, NUM_TRAIN_TIMESTEPS // num_sampling,
+                        torch.cat([torch.tensor([1.0]), abar]), abar[0].clone())
+
+    def alpha(self, t) -> torch.Tensor:
+        """StableDiffusion.alpha, latent_diffusion.py:88-90."""
+        t = int(t)
+        return self.alphas_cumprod[t] if t >= 0 else self.final_alpha_cumprod
+
+
+def _state(t: float, in_scale: float, lam: float, c=(0, 0, 0, 0), d=(0, 0, 0, 0), second_order=0) -> StepStateC:
+    s = StepStateC()
+    s.t, s.in_scale = float(t), float(in_scale)
+    s.coef.lambda_ = float(np.float32(lam))
+    s.coef.c0, s.coef.c1, s.coef.c2, s.coef.c3 = (float(x) for x in c)
+    s.coef.d0, s.coef.d1, s.coef.d2, s.coef.d3 = (float(x) for x in d)
+    s.coef.second_order = int(second_order)
+    return s
+
+
+def ddim_cfgpp_steps(sch: Schedule, cfg_guidance: float, sdxl_indexing: bool) -> List[StepStateC]:
+    """Sampling loop scalars. sdxl_indexing: `alphas_cumprod[t - skip]` with Python negative-index wrap on the last
+    step (latent_sdxl.py:732-734); otherwise StableDiffusion.alpha() (negative -> final_alpha_cumprod)."""
+    out = []
+    for t in sch.timesteps.int():
+        if sdxl_indexing:
+            at, at_next = sch.alphas_cumprod[t], sch.alphas_cumprod[t - sch.skip]
+        else:
+            at, at_next = sch.alpha(t), sch.alpha(t - sch.skip)
+        out.append(_state(float(t), 1.0, cfg_guidance,
+                          c=((1 - at).sqrt(), at.sqrt(), at_next.sqrt(), (1 - at_next).sqrt())))
+    return out
+
+
+def ddim_inversion_cfgpp_steps(sch: Schedule, cfg_guidance: float) -> List[StepStateC]:
+    """InversionDDIMCFGpp.inversion scalars, latent_diffusion.py:897-908 (ascending t)."""
+    out = []
+    for t in reversed(sch.timesteps):
+        at, at_prev = sch.alpha(t), sch.alpha(t - sch.skip)
+        out.append(_state(float(t), 1.0, cfg_guidance,
+                          c=((1 - at_prev).sqrt(), at_prev.sqrt(), at.sqrt(), (1 - at).sqrt())))
+    return out
+
+
+def sigma_to_t(sch: Schedule, sigma: torch.Tensor) -> torch.Tensor:
+    """SDXL.sigma_to_t, quantize=True (latent_sdxl.py:333-339)."""
+    total_sigmas = (1 - sch.total_alphas).sqrt() / sch.total_alphas.sqrt()
+    dists = sigma - total_sigmas[:, None]
+    return dists.abs().argmin(dim=0).view(sigma.shape)
+
+
+def dpmpp_2m_cfgpp_steps(sch: Schedule, cfg_guidance: float):
+    """DPMpp2mCFGppSolver.reverse_process scalars (latent_sdxl.py:877-918). Returns (steps, sigma0)."""
+    alphas = sch.alphas_cumprod[sch.timesteps.int()]
+    sigmas = (1 - alphas).sqrt() / alphas.sqrt()
+    t_fn = lambda s: s.log().neg()  # noqa: E731
+    out = []
+    n = len(sch.timesteps) - 1
+    for i in range(n):
+        at, sigma = alphas[i], sigmas[i]
+        c_in, c_out = at.clone().sqrt(), -sigma.clone()
+        new_t = sigma_to_t(sch, sigma)
+        t, t_next = t_fn(sigmas[i]), t_fn(sigmas[i + 1])
+        h = t_next - t
+        inv_sigma = torch.tensor(1.0, dtype=torch.float32) / torch.tensor(sigmas[i].item(), dtype=torch.float32)
+        if i == 0 or sigmas[i + 1] == 0:
+            out.append(_state(float(new_t), c_in, cfg_guidance, c=(c_out, inv_sigma, sigmas[i + 1], 0.0)))
+        else:
+            h_last = t - t_fn(sigmas[i - 1])
+            r = h_last / h
+            inv_2r = torch.tensor(1.0, dtype=torch.float32) / (2 * r)
+            out.append(_state(float(new_t), c_in, cfg_guidance, c=(c_out, inv_sigma, sigmas[i + 1], 0.0),
+                              d=(-torch.exp(-h), (-h).expm1(), inv_2r, torch.exp(-h)), second_order=1))
+    return out, sigmas[0]
+
+
+def to_c_array(steps: List[StepStateC]):
+    arr = (StepStateC * len(steps))()
+    for i, s in enumerate(steps):
+        arr[i] = s
+    return arr

@@ -251,6 +251,182 @@ def bench_gemm():
             print(f"[EXC] bench conv: {e}", flush=True)
 
 
+def diag_attn():
+    g = torch.Generator(device="cpu").manual_seed(3)
+    cases = [(1, 1, 128, 128), (2, 2, 256, 256), (1, 4, 64, 64), (2, 5, 1024, 1024), (1, 10, 4096, 4096),
+             (2, 4, 256, 77), (4, 20, 1024, 77), (1, 2, 200, 333)]
+    for (B, H, Nq, Nkv) in cases:
+        name = f"attention B={B} H={H} Nq={Nq} Nkv={Nkv}"
+
+        def run():
+            C = H * 64
+            if Nq == Nkv:
+                qkv = (torch.randn(B, Nq, 3 * C, generator=g) * 1.2).half().to(dev)
+                q, k, v = qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
+            else:
+                q = (torch.randn(B, Nq, C, generator=g) * 1.2).half().to(dev)
+                kv = (torch.randn(B, Nkv, 2 * C, generator=g) * 1.2).half().to(dev)
+                k, v = kv[:, :, :C], kv[:, :, C:]
+            out = nv.op_attention(q, k, v, H)
+            qf, kf, vf = (t.float().reshape(B, -1, H, 64).transpose(1, 2) for t in (q, k, v))
+            ref = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf)
+            ref = ref.transpose(1, 2).reshape(B, Nq, C)
+            report(name, out, ref, tol=3e-3)
+
+        guarded(name, run)
+
+
+def diag_norm():
+    g = torch.Generator(device="cpu").manual_seed(4)
+
+    def rnd(*s, scale=1.0, shift=0.0):
+        return (torch.randn(*s, generator=g) * scale + shift).half().to(dev)
+
+    for (B, HW, C1, C2, silu, eps) in [(2, 1024, 64, 0, True, 1e-5), (4, 16384, 320, 0, True, 1e-5),
+                                       (2, 4096, 640, 320, True, 1e-5), (4, 1024, 1280, 1280, True, 1e-5),
+                                       (2, 1024, 1280, 640, False, 1e-6), (2, 64, 256, 0, False, 1e-6)]:
+        name = f"groupnorm B={B} HW={HW} C={C1}+{C2} silu={silu}"
+
+        def run():
+            x1 = rnd(B, HW, C1, scale=2.0, shift=0.5)
+            x2 = rnd(B, HW, C2, scale=0.7, shift=-0.3) if C2 else None
+            C = C1 + C2
+            gamma, beta = rnd(C, scale=0.2, shift=1.0), rnd(C, scale=0.2)
+            out = nv.op_groupnorm(x1, gamma, beta, eps, silu, x2)
+            x = torch.cat([x1, x2], 2) if C2 else x1
+            xn = x.float().permute(0, 2, 1).reshape(B, C, HW, 1)
+            ref = torch.nn.functional.group_norm(xn, 32, gamma.float(), beta.float(), eps)
+            if silu:
+                ref = torch.nn.functional.silu(ref)
+            ref = ref.reshape(B, C, HW).permute(0, 2, 1).half()
+            report(name, out, ref, tol=1e-3)
+
+        guarded(name, run)
+    for (M, C) in [(4096, 1280), (16384, 640), (300, 128), (64, 256)]:
+        name = f"layernorm M={M} C={C}"
+
+        def run():
+            x = rnd(M, C, scale=3.0, shift=1.0)
+            gamma, beta = rnd(C, scale=0.2, shift=1.0), rnd(C, scale=0.2)
+            out = nv.op_layernorm(x, gamma, beta)
+            ref = torch.nn.functional.layer_norm(x.float(), (C,), gamma.float(), beta.float(), 1e-5).half()
+            report(name, out, ref, tol=1e-3)
+
+        guarded(name, run)
+
+
+def _oracle_cfg(cfg):
+    import dataclasses
+    from oracle import unet as O
+    return O.UNetConfig(**{f.name: getattr(cfg, f.name) for f in dataclasses.fields(O.UNetConfig)})
+
+
+def _unet_inputs(cfg, B, hw, seed=7):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    z = torch.randn(B, 4, hw, hw, generator=g).to(dev)
+    uc = torch.randn(B, 77, cfg.cross_attention_dim, generator=g).half().to(dev)
+    c = torch.randn(B, 77, cfg.cross_attention_dim, generator=g).half().to(dev)
+    add = None
+    if cfg.addition_embed_type == "text_time":
+        pooled = torch.randn(2 * B, cfg.pooled_dim, generator=g).half().to(dev)
+        tid = torch.tensor([[hw * 8, hw * 8, 0, 0, hw * 8, hw * 8]] * (2 * B), dtype=torch.float16).to(dev)
+        add = {"text_embeds": pooled, "time_ids": tid}
+    return z, uc, c, add
+
+
+def diag_unet(which=("tiny_sdxl", "tiny_sd15")):
+    from cfgpp_b200 import config as C, weights as Wt
+    from cfgpp_b200.engine import NativeUNet
+    from oracle import unet as O
+    for name, B, hw, t in [("tiny_sdxl", 2, 32, 801), ("tiny_sd15", 1, 32, 401), ("tiny_sdxl", 1, 64, 21),
+                           ("sdxl", 1, 128, 501)]:
+        if name not in which:
+            continue
+        label = f"unet {name} B={B} latent={hw} t={t}"
+
+        def run():
+            cfg = C.CONFIGS[name]()
+            sd = Wt.synthetic_state_dict(cfg, seed=1234, device=dev)
+            z, uc, c, add = _unet_inputs(cfg, B, hw)
+            net = NativeUNet(cfg, sd, dev)
+            net.prepare(B, hw, hw)
+            print(f"      workspace {net.workspace_bytes/2**20:.0f} MiB, forward {net.forward_flops/1e12:.3f} TFLOP, "
+                  f"{net.launches_per_step} launches/step", flush=True)
+            net.set_prompt(torch.cat([uc, c]), add["text_embeds"] if add else None,
+                           add["time_ids"].float() if add else None)
+            eu, ec = net.predict_noise(z, float(t))
+            torch.cuda.synchronize()
+            ocfg = _oracle_cfg(cfg)
+            z_in, t_in, ctx = torch.cat([z] * 2), torch.tensor([t] * 2, device=dev), torch.cat([uc, c])
+            m16 = O.build_unet(ocfg, sd, dtype=torch.float16, device=dev)
+            with torch.autocast("cuda", dtype=torch.float16):
+                r16 = m16(z_in, t_in, ctx, add)["sample"]
+            del m16
+            m32 = O.build_unet(ocfg, sd, dtype=torch.float32, device=dev)
+            r32 = m32(z_in, t_in, ctx, {k: v.float() for k, v in add.items()} if add else None)["sample"]
+            del m32
+            got = torch.cat([eu, ec]).float()
+            e_ref = (r16.float() - r32).norm().item() / r32.norm().item()
+            e_got = (got - r32).norm().item() / r32.norm().item()
+            print(f"      std(eps)={r32.std().item():.4f}  relL2(ref16 vs fp32)={e_ref:.3e}  relL2(native vs fp32)={e_got:.3e}",
+                  flush=True)
+            report(label + " vs fp16-autocast oracle", got, r16, tol=5e-3)
+            net.close()
+
+        guarded(label, run)
+
+
+def bench_unet():
+    """First end-to-end timing of the SDXL step (B=2 -> UNet batch 4) vs the eager fp16-autocast oracle."""
+    from cfgpp_b200 import config as C, weights as Wt, schedule as S
+    from cfgpp_b200.engine import NativeUNet
+    from oracle import unet as O
+    cfg = C.sdxl_config()
+    B, hw = 2, 128
+    sd = Wt.synthetic_state_dict(cfg, seed=1234, device=dev)
+    z, uc, c, add = _unet_inputs(cfg, B, hw)
+    net = NativeUNet(cfg, sd, dev)
+    net.prepare(B, hw, hw)
+    net.set_prompt(torch.cat([uc, c]), add["text_embeds"], add["time_ids"].float())
+    sch = S.Schedule.make(50)
+    steps = S.ddim_cfgpp_steps(sch, 0.6, sdxl_indexing=True)
+    net.set_schedule(S.STEP_DDIM_CFGPP, torch.float32, steps)
+    net.set_state(z)
+    net.run_steps(0, 3)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    net.run_steps(3, 10)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(f"native fused step (graph): {ms:.2f} ms/step  -> {net.forward_flops/ms/1e9:.0f} TFLOP/s algorithmic, "
+          f"{B/(50*ms/1e3):.3f} img/s @NFE=50", flush=True)
+    for _ in range(2):
+        net.predict_noise(z, 500.0)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        net.predict_noise(z, 500.0)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"native eager forward: {e0.elapsed_time(e1)/5:.2f} ms", flush=True)
+    net.close()
+    del net
+    m16 = O.build_unet(_oracle_cfg(cfg), sd, dtype=torch.float16, device=dev)
+    z_in, t_in, ctx = torch.cat([z] * 2), torch.tensor([500] * 2, device=dev), torch.cat([uc, c])
+    with torch.autocast("cuda", dtype=torch.float16), torch.no_grad():
+        for _ in range(3):
+            m16(z_in, t_in, ctx, add)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            m16(z_in, t_in, ctx, add)
+        e1.record()
+        torch.cuda.synchronize()
+    print(f"eager torch fp16-autocast oracle forward: {e0.elapsed_time(e1)/5:.2f} ms", flush=True)
+
+
 if __name__ == "__main__":
     which = set(sys.argv[1:]) or {"gemm", "conv", "bench"}
     t0 = time.time()
@@ -261,5 +437,15 @@ if __name__ == "__main__":
         diag_conv()
     if "bench" in which:
         bench_gemm()
+    if "attn" in which:
+        diag_attn()
+    if "norm" in which:
+        diag_norm()
+    if "unet_tiny" in which:
+        diag_unet(("tiny_sdxl", "tiny_sd15"))
+    if "unet_sdxl" in which:
+        diag_unet(("sdxl",))
+    if "bench_unet" in which:
+        bench_unet()
     nbad = sum(1 for _, ok in RESULTS if not ok)
     print(f"=== {len(RESULTS) - nbad}/{len(RESULTS)} cases OK in {time.time() - t0:.1f}s ===", flush=True)
