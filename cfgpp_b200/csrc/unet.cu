@@ -702,7 +702,6 @@ void Unet::set_state(const void* z, int z_dtype, cudaStream_t stream) {
   const size_t lat = static_cast<size_t>(B_) * 4 * H_ * W_;
   const size_t es = (state_dtype_ == CFGPP_F16) ? 2 : 4;
   CFGPP_CHECK_CUDA(cudaMemcpyAsync(z_state_, z, lat * es, cudaMemcpyDeviceToDevice, stream));
-  CFGPP_CHECK_CUDA(cudaMemsetAsync(aux_state_, 0, lat * es, stream));
 }
 
 void Unet::ensure_graph(cudaStream_t stream) {

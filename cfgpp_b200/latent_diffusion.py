@@ -1,0 +1,191 @@
+"""Stable Diffusion v1.5 CFG++ solvers on the Blackwell-native backend.
+
+Mirror of the reference's `latent_diffusion.py` solver API for the hot path: registry (:13-26), `StableDiffusion`
+base (:54-241: `alpha`, `get_text_embed`, `encode`, `decode`, `predict_noise`, `inversion`, `initialize_latent`),
+`ddim_cfg++` (:621-679) and `ddim_inversion_cfg++` (:882-957). Same names, argument meaning and errors; the UNet
+forward, CFG++ mix and DDIM update run in hand-written sm_100a CUDA behind include/cfgpp_b200.h.
+
+dtype note (reference promotion rules): `ddim_cfg++` keeps an fp32 latent state (zT is a fp32
+`torch.randn`); `ddim_inversion_cfg++` starts from the fp16 VAE latent, so both its inversion loop and the following
+sampling loop run with an fp16 state — every update op rounds to fp16, which the fused step kernel reproduces.
+"""
+from __future__ import annotations
+
+from typing import Any, Optional
+
+import torch
+
+from . import schedule as S
+from .conditioning import LatentPreviewDecoder, SyntheticTextEncoder
+from .config import UNetConfig, sd15_config
+from .latent_sdxl import _Scheduler, get_engine
+
+####### Factory #######
+__SOLVER__ = {}
+
+
+def register_solver(name: str):
+    def wrapper(cls):
+        if __SOLVER__.get(name, None) is not None:
+            raise ValueError(f"Solver {name} already registered.")
+        __SOLVER__[name] = cls
+        return cls
+    return wrapper
+
+
+def get_solver(name: str, **kwargs):
+    if name not in __SOLVER__:
+        raise ValueError(f"Solver {name} does not exist.")
+    return __SOLVER__[name](**kwargs)
+
+########################
+
+
+class StableDiffusion():
+    def __init__(self,
+                 solver_config,
+                 model_key: str = "runwayml/stable-diffusion-v1-5",
+                 device: Optional[torch.device] = None,
+                 **kwargs):
+        self.device = device
+        self.dtype = kwargs.get("pipe_dtype", torch.float16)
+        self.cfg: UNetConfig = kwargs.get("unet_config") or sd15_config()
+        self.unet = get_engine(model_key, self.cfg, device, kwargs.get("state_dict"))
+        self.text_encoder = kwargs.get("text_encoder") or SyntheticTextEncoder(self.cfg.cross_attention_dim, 0)
+        self.vae = kwargs.get("vae") or LatentPreviewDecoder(self.cfg.vae_scale_factor)
+
+        self._sch = S.Schedule.make(solver_config.num_sampling, "ddim")
+        self.total_alphas = self._sch.total_alphas
+        self.sigmas = self._sch.sigmas
+        self.log_sigmas = self._sch.log_sigmas
+        self.skip = self._sch.skip
+        self.final_alpha_cumprod = self._sch.final_alpha_cumprod
+        self.scheduler = _Scheduler(self._sch, device)
+        self._prompt_key = None
+
+    def __call__(self, *args: Any, **kwargs: Any) -> Any:
+        self.sample(*args, **kwargs)
+
+    def sample(self, *args: Any, **kwargs: Any) -> Any:
+        raise NotImplementedError("Solver must implement sample() method.")
+
+    def alpha(self, t):
+        return self._sch.alpha(t)
+
+    @torch.no_grad()
+    def get_text_embed(self, null_prompt, prompt):
+        null_text_embed, _ = self.text_encoder(null_prompt, self.device)
+        text_embed, _ = self.text_encoder(prompt, self.device)
+        return null_text_embed, text_embed
+
+    def encode(self, x):
+        return self.vae.encode(x, self.dtype)
+
+    def decode(self, zt):
+        return self.vae.decode(zt).float()
+
+    def _prepare(self, zt, uc, c):
+        b, _, h, w = zt.shape
+        if (b, (h, w)) != (self.unet.batch, self.unet.latent_hw):
+            self.unet.prepare(b, h, w)
+            self._prompt_key = None
+        key = (uc.data_ptr(), c.data_ptr(), uc._version, c._version)
+        if key != self._prompt_key:
+            self.unet.set_prompt(torch.cat([uc, c], dim=0))
+            self._prompt_key = key
+
+    def predict_noise(self, zt: torch.Tensor, t: torch.Tensor, uc: torch.Tensor, c: torch.Tensor):
+        if uc is None or c is None:
+            uc = c if uc is None else uc
+            c = uc if c is None else c
+        self._prepare(zt, uc, c)
+        return self.unet.predict_noise(zt, float(t))
+
+    def _run(self, method, steps, z_init, uc, c, callback_fn=None):
+        self._prepare(z_init, uc, c)
+        eng = self.unet
+        eng.set_schedule(method, z_init.dtype, steps)
+        eng.set_state(z_init)
+        z0t = None
+        if callback_fn is None:
+            eng.run_steps(0, len(steps))
+            z0t = eng.get_state(1)
+        else:
+            for i, st in enumerate(steps):
+                eps_uc, eps_c = eng.predict_noise(eng.get_state(0), st.t)
+                eng.apply_step(i, eps_uc, eps_c)
+                kw = {'z0t': eng.get_state(1).detach(), 'zt': eng.get_state(0).detach(), 'decode': self.decode}
+                kw = callback_fn(i, torch.tensor(int(st.t), device=self.device), kw)
+                z0t = kw['z0t']
+                eng.set_state(kw['zt'])
+        return z0t, eng.get_state(0)
+
+    @torch.no_grad()
+    def inversion(self, z0: torch.Tensor, uc: torch.Tensor, c: torch.Tensor, cfg_guidance: float = 1.0):
+        raise NotImplementedError("plain-CFG DDIM inversion is outside the CFG++ hot-path scope (SURVEY §8 f4)")
+
+    def initialize_latent(self, method: str = 'random', src_img: Optional[torch.Tensor] = None, **kwargs):
+        if method == 'ddim':
+            z = self.inversion(self.encode(src_img.to(self.dtype).to(self.device)), kwargs.get('uc'), kwargs.get('c'),
+                               cfg_guidance=kwargs.get('cfg_guidance', 0.0))
+        elif method == 'npi':
+            z = self.inversion(self.encode(src_img.to(self.dtype).to(self.device)), kwargs.get('c'), kwargs.get('c'),
+                               cfg_guidance=1.0)
+        elif method == 'random':
+            size = kwargs.get('latent_dim', (1, 4, self.cfg.sample_size, self.cfg.sample_size))
+            z = torch.randn(size).to(self.device)  # CPU generator, then H2D — latent_diffusion.py:199-200
+        elif method == 'random_kdiffusion':
+            size = kwargs.get('latent_dim', (1, 4, self.cfg.sample_size, self.cfg.sample_size))
+            sigmas = kwargs.get('sigmas', [14.6146])
+            z = torch.randn(size).to(self.device)
+            z = z * (sigmas[0] ** 2 + 1) ** 0.5
+        else:
+            raise NotImplementedError
+        return z
+
+
+###########################################
+# CFG++ version
+###########################################
+
+@register_solver("ddim_cfg++")
+class BaseDDIMCFGpp(StableDiffusion):
+    """DDIM solver for SD with CFG++ (text-to-image)."""
+
+    def reverse_process(self, uc, c, cfg_guidance, zt, callback_fn=None):
+        steps = S.ddim_cfgpp_steps(self._sch, cfg_guidance, sdxl_indexing=False)
+        z0t, _ = self._run(S.STEP_DDIM_CFGPP, steps, zt, uc, c, callback_fn)
+        return z0t
+
+    def sample(self, cfg_guidance=7.5, prompt=["", ""], callback_fn=None, **kwargs):
+        uc, c = self.get_text_embed(null_prompt=prompt[0], prompt=prompt[1])
+        zt = kwargs.get('zT')
+        if zt is None:
+            zt = self.initialize_latent()
+        z0t = self.reverse_process(uc, c, cfg_guidance, zt, callback_fn)
+        img = self.decode(z0t)
+        img = (img / 2 + 0.5).clamp(0, 1)
+        return img.detach().cpu()
+
+
+@register_solver("ddim_inversion_cfg++")
+class InversionDDIMCFGpp(BaseDDIMCFGpp):
+    """Editing via WordSwap after inversion (CFG++ inversion: Tweedie with eps_uc, renoise with the guided eps)."""
+
+    @torch.no_grad()
+    def inversion(self, z0: torch.Tensor, uc: torch.Tensor, c: torch.Tensor, cfg_guidance: float = 1.0):
+        steps = S.ddim_inversion_cfgpp_steps(self._sch, cfg_guidance)
+        _, zt = self._run(S.STEP_DDIM_INV_CFGPP, steps, z0.clone().to(self.device), uc, c)
+        return zt
+
+    def sample(self, src_img, cfg_guidance=7.5, prompt=["", ""], callback_fn=None, **kwargs):
+        uc, c = self.get_text_embed(null_prompt=prompt[0], prompt=prompt[1])
+        zt = self.initialize_latent(method='ddim', src_img=src_img, uc=uc, c=c, cfg_guidance=cfg_guidance)
+        z0t = self.reverse_process(uc, c, cfg_guidance, zt, callback_fn)
+        img = self.decode(z0t)
+        img = (img / 2 + 0.5).clamp(0, 1)
+        return img.detach().cpu()
+
+
+if __name__ == "__main__":
+    print(f"Possble solvers: {[x for x in __SOLVER__.keys()]}")

@@ -1,0 +1,376 @@
+"""SDXL / SDXL-Lightning CFG++ solvers on the Blackwell-native backend.
+
+Mirror of the reference's `latent_sdxl.py` solver API for the hot path named by BASELINE.json — same registry
+(`register_solver` / `get_solver`, latent_sdxl.py:15-28), same class / method names and argument meaning
+(`SDXL.sample` :200-266, `reverse_process` :715-755 / :843-858 / :864-930, `predict_noise` :167-185,
+`initialize_latent` :268-299, `sigma_to_t` :333-346), same errors (ValueError for unknown / duplicate solver,
+AssertionError for Lightning with cfg_guidance != 1, NotImplementedError for unknown init methods) — but the UNet
+forward, the CFG++ guidance mix and the scheduler update run in hand-written sm_100a CUDA behind the C ABI
+(include/cfgpp_b200.h). With `callback_fn=None` a whole trajectory is enqueued as NFE replays of one CUDA graph with
+no host synchronisation; with a callback the un-fused seam (`predict_noise` + `apply_step`) is used so that `z0t` /
+`zt` are materialised and may be replaced by the callback, exactly like the reference loop.
+
+Registered here: ddim_cfg++, ddim_cfg++_lightning, dpm++_2m_cfgpp (the solvers of SURVEY.md §8a). Text encoders and
+the VAE stay on the reference path (see conditioning.py).
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Any, Optional, Tuple
+
+import torch
+
+from . import schedule as S
+from .conditioning import LatentPreviewDecoder, SyntheticTextEncoder
+from .config import UNetConfig, sdxl_config
+from .engine import NativeUNet
+from .weights import load_safetensors_state_dict, synthetic_state_dict
+
+####### Factory #######
+__SOLVER__ = {}
+
+
+def register_solver(name: str):
+    def wrapper(cls):
+        if __SOLVER__.get(name, None) is not None:
+            raise ValueError(f"Solver {name} already registered.")
+        __SOLVER__[name] = cls
+        return cls
+    return wrapper
+
+
+def get_solver(name: str, **kwargs):
+    if name not in __SOLVER__:
+        raise ValueError(f"Solver {name} does not exist.")
+    return __SOLVER__[name](**kwargs)
+
+########################
+
+_ENGINES = {}
+
+
+def resolve_state_dict(model_key: str, cfg: UNetConfig, device):
+    """`*.safetensors` path -> real weights; 'synthetic[:seed]' -> seeded synthetic; anything else (an HF hub id:
+    nothing can be downloaded here) -> synthetic with a warning."""
+    if model_key.endswith(".safetensors"):
+        return load_safetensors_state_dict(model_key, device=device)
+    seed = 1234
+    if model_key.startswith("synthetic"):
+        if ":" in model_key:
+            seed = int(model_key.split(":", 1)[1])
+    else:
+        warnings.warn(f"no checkpoint for '{model_key}' is available offline; using seeded synthetic UNet weights "
+                      f"(pass a diffusers-format *.safetensors path as model_key for real weights)")
+    return synthetic_state_dict(cfg, seed=seed, device=device)
+
+
+def get_engine(model_key: str, cfg: UNetConfig, device, state_dict=None) -> NativeUNet:
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("cfgpp_b200 solvers run on CUDA (sm_100a) only — there is no CPU fallback on the product "
+                           "path; the CPU eager baseline lives in oracle/ and bench.py")
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (model_key, cfg.name, idx, id(state_dict) if state_dict is not None else None)
+    if key not in _ENGINES:
+        sd = state_dict if state_dict is not None else resolve_state_dict(model_key, cfg, torch.device("cuda", idx))
+        _ENGINES[key] = NativeUNet(cfg, sd, torch.device("cuda", idx))
+    return _ENGINES[key]
+
+
+class _Scheduler:
+    """The two attributes of the diffusers scheduler object the reference touches."""
+    def __init__(self, sch: S.Schedule, device):
+        self.timesteps = sch.timesteps.to(device)
+        self.alphas_cumprod = sch.alphas_cumprod
+        self.final_alpha_cumprod = sch.final_alpha_cumprod
+
+
+class SDXL():
+    schedule_kind = "ddim"
+    quantize = True
+
+    def __init__(self,
+                 solver_config,
+                 model_key: str = "stabilityai/stable-diffusion-xl-base-1.0",
+                 dtype=torch.float16,
+                 device='cuda',
+                 unet_config: Optional[UNetConfig] = None,
+                 state_dict=None,
+                 text_encoders=None,
+                 vae=None):
+        self.device = device
+        self.dtype = dtype
+        self.cfg = unet_config or sdxl_config()
+        self.unet = get_engine(model_key, self.cfg, device, state_dict)
+
+        d1 = self.cfg.cross_attention_dim - self.cfg.pooled_dim
+        self.text_enc_1, self.text_enc_2 = text_encoders or (
+            SyntheticTextEncoder(d1 if d1 > 0 else self.cfg.cross_attention_dim // 2, 0),
+            SyntheticTextEncoder(self.cfg.cross_attention_dim - (d1 if d1 > 0 else self.cfg.cross_attention_dim // 2),
+                                 self.cfg.pooled_dim))
+        self.vae = vae or LatentPreviewDecoder(self.cfg.vae_scale_factor)
+        self.vae_scale_factor = self.cfg.vae_scale_factor
+        self.default_sample_size = self.cfg.sample_size
+
+        # sampling parameters (latent_sdxl.py:56-67 / :407-418)
+        self._sch = S.Schedule.make(solver_config.num_sampling, self.schedule_kind)
+        self.total_alphas = self._sch.total_alphas
+        self.sigmas = self._sch.sigmas
+        self.log_sigmas = self._sch.log_sigmas
+        self.skip = self._sch.skip
+        self.final_alpha_cumprod = self._sch.final_alpha_cumprod
+        self.scheduler = _Scheduler(self._sch, device)
+        self._prompt_key = None
+
+    def __call__(self, *args: Any, **kwargs: Any) -> Any:
+        self.sample(*args, **kwargs)
+
+    def alpha(self, t):
+        at = self.scheduler.alphas_cumprod[t] if t >= 0 else self.final_alpha_cumprod
+        return at
+
+    @torch.no_grad()
+    def _text_embed(self, prompt, text_enc, clip_skip):
+        prompt = prompt[0] if isinstance(prompt, (list, tuple)) else prompt
+        return text_enc(prompt, self.device)
+
+    @torch.no_grad()
+    def get_text_embed(self, null_prompt_1, prompt_1, null_prompt_2=None, prompt_2=None, clip_skip=None):
+        prompt_embed_1, pool_prompt_embed = self._text_embed(prompt_1, self.text_enc_1, clip_skip)
+        if prompt_2 is None:
+            prompt_embed = [prompt_embed_1]
+        else:
+            prompt_embed_2, pool_prompt_embed = self._text_embed(prompt_2, self.text_enc_2, clip_skip)
+            prompt_embed = [prompt_embed_1, prompt_embed_2]
+        null_embed_1, pool_null_embed = self._text_embed(null_prompt_1, self.text_enc_1, clip_skip)
+        if null_prompt_2 is None:
+            null_embed = [null_embed_1]
+        else:
+            null_embed_2, pool_null_embed = self._text_embed(null_prompt_2, self.text_enc_2, clip_skip)
+            null_embed = [null_embed_1, null_embed_2]
+        null_prompt_embeds = torch.concat(null_embed, dim=-1)
+        prompt_embeds = torch.concat(prompt_embed, dim=-1)
+        return null_prompt_embeds, prompt_embeds, pool_null_embed, pool_prompt_embed
+
+    @torch.no_grad()
+    def encode(self, x):
+        return self.vae.encode(x, self.dtype)
+
+    def decode(self, zt):
+        return self.vae.decode(zt).float()
+
+    # ---- the seam: batched (uncond + cond) UNet forward on the native backend -----------------------------------
+    def _bind_prompt(self, uc, c, added_cond_kwargs):
+        key = (uc.data_ptr(), c.data_ptr(), uc._version, c._version,
+               None if not added_cond_kwargs else added_cond_kwargs['text_embeds'].data_ptr())
+        if key == self._prompt_key:
+            return
+        ctx = torch.cat([uc, c], dim=0)
+        if self.cfg.addition_embed_type == "text_time":
+            self.unet.set_prompt(ctx, added_cond_kwargs['text_embeds'], added_cond_kwargs['time_ids'].float())
+        else:
+            self.unet.set_prompt(ctx)
+        self._prompt_key = key
+
+    def _prepare(self, zt, uc, c, added_cond_kwargs):
+        b, _, h, w = zt.shape
+        if (b, (h, w)) != (self.unet.batch, self.unet.latent_hw):
+            self.unet.prepare(b, h, w)
+            self._prompt_key = None
+        self._bind_prompt(uc, c, added_cond_kwargs)
+
+    def predict_noise(self, zt, t, uc, c, added_cond_kwargs, in_scale: float = 1.0):
+        if uc is None or c is None:
+            # single-branch paths of the reference (latent_sdxl.py:169-176) are never taken by the CFG++ solvers
+            uc = c if uc is None else uc
+            c = uc if c is None else c
+        self._prepare(zt, uc, c, added_cond_kwargs)
+        return self.unet.predict_noise(zt, float(t), in_scale)
+
+    def _get_add_time_ids(self, original_size, crops_coords_top_left, target_size, dtype, text_encoder_projection_dim):
+        add_time_ids = list(original_size + crops_coords_top_left + target_size)
+        passed_add_embed_dim = self.cfg.addition_time_embed_dim * len(add_time_ids) + text_encoder_projection_dim
+        expected_add_embed_dim = self.cfg.projection_class_embeddings_input_dim
+        assert expected_add_embed_dim == passed_add_embed_dim, (
+            f"Model expects an added time embedding vector of length {expected_add_embed_dim}, but a vector of "
+            f"{passed_add_embed_dim} was created. The model has an incorrect config.")
+        return torch.tensor([add_time_ids], dtype=dtype)
+
+    def sample(self,
+               prompt1=["", ""],
+               prompt2=["", ""],
+               cfg_guidance: float = 5.0,
+               original_size: Optional[Tuple[int, int]] = None,
+               crops_coords_top_left: Tuple[int, int] = (0, 0),
+               target_size: Optional[Tuple[int, int]] = None,
+               negative_original_size: Optional[Tuple[int, int]] = None,
+               negative_crops_coords_top_left: Tuple[int, int] = (0, 0),
+               negative_target_size: Optional[Tuple[int, int]] = None,
+               clip_skip: Optional[int] = None,
+               **kwargs):
+        height = self.default_sample_size * self.vae_scale_factor
+        width = self.default_sample_size * self.vae_scale_factor
+        original_size = original_size or (height, width)
+        target_size = target_size or (height, width)
+
+        (null_prompt_embeds, prompt_embeds, pool_null_embed, pool_prompt_embed) = self.get_text_embed(
+            prompt1[0], prompt1[1], prompt2[0], prompt2[1], clip_skip)
+
+        add_text_embeds = pool_prompt_embed
+        add_time_ids = self._get_add_time_ids(original_size, crops_coords_top_left, target_size,
+                                              dtype=prompt_embeds.dtype,
+                                              text_encoder_projection_dim=int(pool_prompt_embed.shape[-1]))
+        if negative_original_size is not None and negative_target_size is not None:
+            negative_add_time_ids = self._get_add_time_ids(negative_original_size, negative_crops_coords_top_left,
+                                                           negative_target_size, dtype=prompt_embeds.dtype,
+                                                           text_encoder_projection_dim=int(pool_prompt_embed.shape[-1]))
+        else:
+            negative_add_time_ids = add_time_ids
+        negative_text_embeds = pool_null_embed
+
+        if cfg_guidance != 0.0 and cfg_guidance != 1.0:
+            add_text_embeds = torch.cat([negative_text_embeds, add_text_embeds], dim=0)
+            add_time_ids = torch.cat([negative_add_time_ids, add_time_ids], dim=0)
+
+        add_cond_kwargs = {'text_embeds': add_text_embeds.to(self.device), 'time_ids': add_time_ids.to(self.device)}
+
+        zt = self.reverse_process(null_prompt_embeds, prompt_embeds, cfg_guidance, add_cond_kwargs, target_size,
+                                  **kwargs)
+        with torch.no_grad():
+            img = self.decode(zt)
+        img = (img / 2 + 0.5).clamp(0, 1)
+        return img.detach().cpu()
+
+    def initialize_latent(self, method: str = 'random', src_img: Optional[torch.Tensor] = None,
+                          add_cond_kwargs: Optional[dict] = None, **kwargs):
+        if method == 'random':
+            size = kwargs.get('size', (1, 4, 128, 128))
+            z = torch.randn(size).to(self.device)  # CPU generator, then H2D — latent_sdxl.py:288-289
+        elif method == 'random_kdiffusion':
+            size = kwargs.get('latent_dim', (1, 4, 128, 128))
+            sigmas = kwargs.get('sigmas', [14.6146])
+            z = torch.randn(size).to(self.device)
+            z = z * (sigmas[0] ** 2 + 1) ** 0.5
+        elif method in ('ddim', 'npi'):
+            raise NotImplementedError("SDXL inversion (ddim_edit*) is outside the CFG++ hot-path scope (SURVEY §8 f1)")
+        else:
+            raise NotImplementedError
+        return z
+
+    def reverse_process(self, *args, **kwargs):
+        raise NotImplementedError
+
+    def sigma_to_t(self, sigma, quantize=None):
+        quantize = self.quantize if quantize is None else quantize
+        if not quantize:
+            raise NotImplementedError("only the quantized sigma_to_t is used by the CFG++ solvers")
+        return S.sigma_to_t(self._sch, sigma)
+
+    # ---- shared trajectory driver -------------------------------------------------------------------------------
+    def _run_trajectory(self, method, state_dtype, steps, z_init, uc, c, add_cond_kwargs, callback_fn, result):
+        """`result`: 'z0t' (DDIM family returns the Tweedie estimate of the last step) or 'zt' (DPM++ returns x)."""
+        self._prepare(z_init, uc, c, add_cond_kwargs)
+        eng = self.unet
+        eng.set_schedule(method, state_dtype, steps)
+        eng.set_state(z_init)
+        if callback_fn is None:
+            eng.run_steps(0, len(steps))
+        else:
+            for i, st in enumerate(steps):
+                zt = eng.get_state(0)
+                eps_uc, eps_c = eng.predict_noise(zt, st.t, st.in_scale)
+                eng.apply_step(i, eps_uc, eps_c)
+                kw = {'z0t': eng.get_state(1).detach(), 'zt': eng.get_state(0).detach(), 'decode': self.decode}
+                kw = callback_fn(i, torch.tensor(int(st.t), device=self.device), kw)
+                eng.set_state(kw['zt'])
+                self._cb_z0t = kw['z0t']
+            if result == 'z0t':
+                return self._cb_z0t
+        return eng.get_state(1 if result == 'z0t' else 0)
+
+
+class SDXLLightning(SDXL):
+    schedule_kind = "lightning"
+
+    def __init__(self,
+                 solver_config,
+                 base_model_key: str = "stabilityai/stable-diffusion-xl-base-1.0",
+                 light_model_ckpt: str = "ckpt/sdxl_lightning_4step_unet.safetensors",
+                 dtype=torch.float16,
+                 device='cuda',
+                 **kwargs):
+        import os
+        key = light_model_ckpt if os.path.exists(light_model_ckpt) else "synthetic:4321"
+        if key.startswith("synthetic"):
+            warnings.warn(f"Lightning checkpoint '{light_model_ckpt}' not found; using seeded synthetic UNet weights")
+        SDXL.__init__(self, solver_config, model_key=key, dtype=dtype, device=device, **kwargs)
+
+
+###########################################
+# CFG++ version
+###########################################
+
+@register_solver("ddim_cfg++")
+class BaseDDIMCFGpp(SDXL):
+    def reverse_process(self,
+                        null_prompt_embeds,
+                        prompt_embeds,
+                        cfg_guidance,
+                        add_cond_kwargs,
+                        shape=(1024, 1024),
+                        callback_fn=None,
+                        **kwargs):
+        b = null_prompt_embeds.shape[0]
+        zt = kwargs.get('zT')
+        if zt is None:
+            zt = self.initialize_latent(size=(b, 4, shape[1] // self.vae_scale_factor, shape[0] // self.vae_scale_factor))
+        steps = S.ddim_cfgpp_steps(self._sch, cfg_guidance, sdxl_indexing=True)
+        # fp32 state: zt comes from torch.randn (fp32) and promotes every update (latent_sdxl.py:289, 741-744)
+        return self._run_trajectory(S.STEP_DDIM_CFGPP, torch.float32, steps, zt.float(), null_prompt_embeds,
+                                    prompt_embeds, add_cond_kwargs, callback_fn, 'z0t')
+
+
+@register_solver('ddim_cfg++_lightning')
+class BaseDDIMCFGppLight(BaseDDIMCFGpp, SDXLLightning):
+    def __init__(self, **kwargs):
+        SDXLLightning.__init__(self, **kwargs)
+
+    def reverse_process(self,
+                        null_prompt_embeds,
+                        prompt_embeds,
+                        cfg_guidance,
+                        add_cond_kwargs,
+                        shape=(1024, 1024),
+                        callback_fn=None,
+                        **kwargs):
+        assert cfg_guidance == 1.0, "CFG should be turned off in the lightning version"
+        return super().reverse_process(null_prompt_embeds, prompt_embeds, cfg_guidance, add_cond_kwargs, shape,
+                                       callback_fn, **kwargs)
+
+
+@register_solver('dpm++_2m_cfgpp')
+class DPMpp2mCFGppSolver(SDXL):
+    quantize = True
+
+    def reverse_process(self,
+                        null_prompt_embeds,
+                        prompt_embeds,
+                        cfg_guidance,
+                        add_cond_kwargs,
+                        shape=(1024, 1024),
+                        callback_fn=None,
+                        **kwargs):
+        b = null_prompt_embeds.shape[0]
+        steps, sigma0 = S.dpmpp_2m_cfgpp_steps(self._sch, cfg_guidance)
+        x = kwargs.get('zT')
+        if x is None:
+            x = self.initialize_latent(method='random', size=(b, 4, shape[1] // self.vae_scale_factor,
+                                                              shape[0] // self.vae_scale_factor))
+        x = x.to(torch.float16)
+        x = x * sigma0  # fp16 tensor x 0-dim fp32 -> fp16 (latent_sdxl.py:882-884)
+        return self._run_trajectory(S.STEP_DPMPP2M_CFGPP, torch.float16, steps, x, null_prompt_embeds, prompt_embeds,
+                                    add_cond_kwargs, callback_fn, 'zt')
+
+
+if __name__ == "__main__":
+    print(f"Possble solvers: {[x for x in __SOLVER__.keys()]}")

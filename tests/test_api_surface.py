@@ -1,0 +1,69 @@
+"""Host-side contract: solver registries (names, errors), the C-ABI library (loads, exports every declared symbol),
+loud failure without CUDA, struct layouts, weight-spec coverage. No GPU compute here."""
+import ctypes
+import re
+from pathlib import Path
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_registries_mirror_reference_names_and_errors():
+    from cfgpp_b200 import latent_diffusion as LD
+    from cfgpp_b200 import latent_sdxl as LX
+    assert {"ddim_cfg++", "ddim_inversion_cfg++"} <= set(LD.__SOLVER__)
+    assert {"ddim_cfg++", "ddim_cfg++_lightning", "dpm++_2m_cfgpp"} <= set(LX.__SOLVER__)
+    with pytest.raises(ValueError, match="does not exist"):
+        LX.get_solver("no_such_solver")
+    with pytest.raises(ValueError, match="already registered"):
+        LX.register_solver("ddim_cfg++")(object)
+    with pytest.raises(ValueError, match="already registered"):
+        LD.register_solver("ddim_cfg++")(object)
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = (ROOT / "include" / "cfgpp_b200.h").read_text()
+    declared = set(re.findall(r"\b(cfgpp_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    from cfgpp_b200 import _native as nv
+    lib = nv.load()
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, f"symbols declared in include/cfgpp_b200.h but not exported: {missing}"
+    assert lib.cfgpp_version() >= 100
+
+
+def test_abi_struct_layouts():
+    from cfgpp_b200.config import ModelDescC
+    from cfgpp_b200.schedule import StepCoefC, StepStateC
+    assert ctypes.sizeof(StepCoefC) == 40 and ctypes.sizeof(StepStateC) == 48
+    assert ctypes.sizeof(ModelDescC) == 4 * (3 + 4 * 3 + 1 + 4 * 2 + 7)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_product_path_fails_loudly_without_cuda():
+    from cfgpp_b200 import latent_sdxl as LX
+    from cfgpp_b200.config import tiny_sdxl_config
+    with pytest.raises(RuntimeError, match="CUDA"):
+        LX.get_solver("ddim_cfg++", solver_config=SimpleNamespace(num_sampling=4), device="cpu",
+                      unet_config=tiny_sdxl_config(), model_key="synthetic:1")
+
+
+def test_product_does_not_import_oracle():
+    for f in (ROOT / "cfgpp_b200").rglob("*.py"):
+        src = f.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+        assert "from .. import oracle" not in src
+
+
+def test_step_coef_tables_are_float32_exact():
+    """The host evaluates the per-step scalars with fp32 torch CPU ops, as the reference loops do."""
+    from cfgpp_b200 import schedule as S
+    sch = S.Schedule.make(50)
+    st = S.ddim_cfgpp_steps(sch, 0.6, True)[7]
+    t = int(st.t)
+    at = sch.alphas_cumprod[t]
+    assert st.coef.c0 == float((1 - at).sqrt()) and st.coef.c1 == float(at.sqrt())
+    assert st.coef.lambda_ == float(torch.tensor(0.6, dtype=torch.float32))

@@ -357,13 +357,13 @@ def diag_unet(which=("tiny_sdxl", "tiny_sd15")):
             eu, ec = net.predict_noise(z, float(t))
             torch.cuda.synchronize()
             ocfg = _oracle_cfg(cfg)
-            z_in, t_in, ctx = torch.cat([z] * 2), torch.tensor([t] * 2, device=dev), torch.cat([uc, c])
+            z_in, t_in, ctx = torch.cat([z] * 2), torch.tensor(t, device=dev), torch.cat([uc, c])
             m16 = O.build_unet(ocfg, sd, dtype=torch.float16, device=dev)
             with torch.autocast("cuda", dtype=torch.float16):
                 r16 = m16(z_in, t_in, ctx, add)["sample"]
             del m16
             m32 = O.build_unet(ocfg, sd, dtype=torch.float32, device=dev)
-            r32 = m32(z_in, t_in, ctx, {k: v.float() for k, v in add.items()} if add else None)["sample"]
+            r32 = m32(z_in, t_in, ctx.float(), {k: v.float() for k, v in add.items()} if add else None)["sample"]
             del m32
             got = torch.cat([eu, ec]).float()
             e_ref = (r16.float() - r32).norm().item() / r32.norm().item()
@@ -414,7 +414,7 @@ def bench_unet():
     net.close()
     del net
     m16 = O.build_unet(_oracle_cfg(cfg), sd, dtype=torch.float16, device=dev)
-    z_in, t_in, ctx = torch.cat([z] * 2), torch.tensor([500] * 2, device=dev), torch.cat([uc, c])
+    z_in, t_in, ctx = torch.cat([z] * 2), torch.tensor(500, device=dev), torch.cat([uc, c])
     with torch.autocast("cuda", dtype=torch.float16), torch.no_grad():
         for _ in range(3):
             m16(z_in, t_in, ctx, add)
