@@ -2,6 +2,9 @@
 #include "capi_util.h"
 #include "unet.cuh"
 
+#include <algorithm>
+#include <cstring>
+
 using namespace cfgpp;
 
 struct cfgpp_handle {
@@ -80,6 +83,26 @@ CFGPP_API int cfgpp_get_state(cfgpp_handle* h, int which, void* out, void* strea
 
 CFGPP_API int cfgpp_apply_step(cfgpp_handle* h, int step, const void* eps_uc, const void* eps_c, void* stream) {
   return guarded([&] { h->unet.apply_step(step, (const __half*)eps_uc, (const __half*)eps_c, (cudaStream_t)stream); });
+}
+
+CFGPP_API int cfgpp_profile_forward(cfgpp_handle* h, const void* z, int z_dtype, float t, float in_scale, int max_n,
+                                    int* n_out, float* ms_out, double* flops_out, int* kind_out, char* names_out,
+                                    int name_stride, void* stream) {
+  return guarded([&] {
+    auto prof = h->unet.profile_forward(z, z_dtype, t, in_scale, (cudaStream_t)stream);
+    const int n = static_cast<int>(prof.size()) < max_n ? static_cast<int>(prof.size()) : max_n;
+    *n_out = n;
+    for (int i = 0; i < n; ++i) {
+      ms_out[i] = prof[i].ms;
+      flops_out[i] = prof[i].flops;
+      kind_out[i] = prof[i].kind;
+      if (names_out && name_stride > 0) {
+        const size_t len = std::min<size_t>(prof[i].name.size(), static_cast<size_t>(name_stride - 1));
+        memcpy(names_out + static_cast<size_t>(i) * name_stride, prof[i].name.data(), len);
+        names_out[static_cast<size_t>(i) * name_stride + len] = 0;
+      }
+    }
+  });
 }
 
 }  // extern "C"

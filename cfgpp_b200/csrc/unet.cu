@@ -219,6 +219,7 @@ void Unet::add_gemm(const std::string& name, const GemmOp& op) {
   PlanStep s;
   s.name = name;
   s.flops = op.flops();
+  s.kind = op.p.conv ? 1 : 0;
   s.fn = [op](cudaStream_t st) { run_gemm_op(op, st); };
   cur_plan_->push_back(std::move(s));
 }
@@ -227,6 +228,7 @@ void Unet::add_attn(const std::string& name, const AttnOp& op) {
   PlanStep s;
   s.name = name;
   s.flops = op.flops();
+  s.kind = 2;
   s.fn = [op](cudaStream_t st) { run_attn_op(op, st); };
   cur_plan_->push_back(std::move(s));
 }
@@ -676,6 +678,46 @@ void Unet::unet_forward(const void* z, int z_dtype, float t, float in_scale, __h
   run_plan(body_plan_, stream);
   run_conv_out_step(final_norm_.p, conv_out_w_, conv_out_b_, B_, H_, W_, final_norm_.C, STEP_NONE, nullptr, nullptr,
                     nullptr, nullptr, eps_uc, eps_c, stream);
+}
+
+std::vector<Unet::ProfEntry> Unet::profile_forward(const void* z, int z_dtype, float t, float in_scale,
+                                                   cudaStream_t stream) {
+  CFGPP_REQUIRE(prepared_, "call cfgpp_prepare first");
+  std::vector<ProfEntry> out;
+  std::vector<cudaEvent_t> evs;
+  auto mark = [&]() {
+    cudaEvent_t e;
+    CFGPP_CHECK_CUDA(cudaEventCreate(&e));
+    CFGPP_CHECK_CUDA(cudaEventRecord(e, stream));
+    evs.push_back(e);
+  };
+  StepState s{};
+  s.t = t;
+  s.in_scale = in_scale;
+  CFGPP_CHECK_CUDA(cudaMemcpyAsync(cur_state_, &s, sizeof(s), cudaMemcpyHostToDevice, stream));
+  mark();
+  for (const auto& st : prologue_plan_) {
+    st.fn(stream);
+    mark();
+    out.push_back({st.name, st.kind, st.flops, 0.f});
+  }
+  run_conv_in(z, z_dtype == CFGPP_F16 ? 1 : 0, &cur_state_->in_scale, conv_in_w_, conv_in_b_, conv_in_out_, B_, H_, W_,
+              d_.block_out_channels[0], 2, stream);
+  mark();
+  out.push_back({"conv_in", 3, 2.0 * NB_ * H_ * W_ * 36.0 * d_.block_out_channels[0], 0.f});
+  for (const auto& st : body_plan_) {
+    st.fn(stream);
+    mark();
+    out.push_back({st.name, st.kind, st.flops, 0.f});
+  }
+  run_conv_out_step(final_norm_.p, conv_out_w_, conv_out_b_, B_, H_, W_, final_norm_.C, STEP_NONE, nullptr, nullptr,
+                    nullptr, nullptr, fwd_eps_uc_, fwd_eps_c_, stream);
+  mark();
+  out.push_back({"conv_out+step", 3, 2.0 * NB_ * H_ * W_ * 36.0 * d_.block_out_channels[0], 0.f});
+  CFGPP_CHECK_CUDA(cudaStreamSynchronize(stream));
+  for (size_t i = 0; i < out.size(); ++i) CFGPP_CHECK_CUDA(cudaEventElapsedTime(&out[i].ms, evs[i], evs[i + 1]));
+  for (auto e : evs) cudaEventDestroy(e);
+  return out;
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -28,6 +28,7 @@ struct PlanStep {
   std::string name;
   double flops = 0.0;  // algorithmic FLOPs of this launch group (0 for non-contraction kernels)
   int launches = 1;
+  int kind = 3;  // 0 linear GEMM, 1 conv3x3 (implicit GEMM), 2 attention, 3 other (norm / elementwise)
   std::function<void(cudaStream_t)> fn;
 };
 
@@ -53,6 +54,14 @@ class Unet {
   void run_steps(int first_step, int nsteps, cudaStream_t stream);
   void get_state(int which, void* out, cudaStream_t stream);
   void apply_step(int step, const __half* eps_uc, const __half* eps_c, cudaStream_t stream);
+  // Eager un-fused forward with a CUDA-event pair around every plan entry (profiling aid for bench.py).
+  struct ProfEntry {
+    std::string name;
+    int kind;
+    double flops;
+    float ms;
+  };
+  std::vector<ProfEntry> profile_forward(const void* z, int z_dtype, float t, float in_scale, cudaStream_t stream);
 
  private:
   // ---- weights ----

@@ -120,6 +120,25 @@ class NativeUNet:
                                                  nv.stream_ptr()))
         return eps_uc, eps_c
 
+    def profile_forward(self, z: torch.Tensor, t: float, in_scale: float = 1.0):
+        """[(name, kind, flops, ms)] per plan entry of one eager forward (CUDA events around every launch group)."""
+        z = z.to(self.device).contiguous()
+        max_n, stride = 4096, 96
+        n = c_int()
+        ms = (c_float * max_n)()
+        fl = (c_double * max_n)()
+        kd = (c_int * max_n)()
+        names = ctypes.create_string_buffer(max_n * stride)
+        with torch.cuda.device(self.device):
+            nv.check(self.lib.cfgpp_profile_forward(self._h, nv.ptr(z), c_int(_dtype_code(z)), c_float(float(t)),
+                                                    c_float(float(in_scale)), c_int(max_n), byref(n), ms, fl, kd, names,
+                                                    c_int(stride), nv.stream_ptr()))
+        out = []
+        for i in range(n.value):
+            nm = names.raw[i * stride:(i + 1) * stride].split(b"\0", 1)[0].decode()
+            out.append((nm, kd[i], fl[i], ms[i]))
+        return out
+
     # ---- fused trajectory ------------------------------------------------------------------------------------
     def set_schedule(self, method: int, state_dtype: torch.dtype, steps: Sequence[StepStateC]):
         arr = to_c_array(list(steps))
@@ -127,7 +146,6 @@ class NativeUNet:
         with torch.cuda.device(self.device):
             nv.check(self.lib.cfgpp_set_schedule(self._h, c_int(method), c_int(code), arr, c_int(len(steps)),
                                                  nv.stream_ptr()))
-            torch.cuda.current_stream().synchronize()  # the host table is staged; keep `arr` alive until then
         self._nsteps = len(steps)
         self._state_dtype = state_dtype
 

@@ -110,6 +110,13 @@ int cfgpp_set_prompt(cfgpp_handle* h, const void* ctx_dev, int n_ctx, const void
 int cfgpp_unet_forward(cfgpp_handle* h, const void* z_dev, int z_dtype, float t, float in_scale, void* eps_uc_dev,
                        void* eps_c_dev, void* stream);
 
+/* Profiling aid: the same un-fused forward with a CUDA-event pair around every plan entry. Arrays are caller-owned
+ * host buffers of max_n entries; kind: 0 linear GEMM, 1 conv3x3, 2 attention, 3 other; names_host holds max_n
+ * NUL-terminated strings of name_stride bytes each (may be NULL). Synchronises the stream (not a hot-path call). */
+int cfgpp_profile_forward(cfgpp_handle* h, const void* z_dev, int z_dtype, float t, float in_scale, int max_n,
+                          int* n_out, float* ms_host, double* flops_host, int* kind_host, char* names_host,
+                          int name_stride, void* stream);
+
 /* ---- fused trajectory: UNet + CFG++ mix + scheduler update per step, one CUDA graph replayed per step -------- */
 int cfgpp_set_schedule(cfgpp_handle* h, int method, int state_dtype, const cfgpp_step_state* steps_host, int nsteps,
                        void* stream);

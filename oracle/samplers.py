@@ -42,6 +42,8 @@ def predict_noise(unet, zt, t, uc, c, added_cond_kwargs=None):
         c_embed = torch.cat([uc, c], dim=0)
         z_in = torch.cat([zt] * 2)
         t_in = torch.cat([t_in] * 2)
+        if zt.shape[0] > 1:  # batch extension (the reference is batch-1): B independent trajectories share t
+            t_in = t.reshape(1).expand(z_in.shape[0])
         noise_pred = unet(z_in, t_in, encoder_hidden_states=c_embed, added_cond_kwargs=added_cond_kwargs)["sample"]
         noise_uc, noise_c = noise_pred.chunk(2)
     return noise_uc, noise_c

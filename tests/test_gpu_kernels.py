@@ -1,0 +1,139 @@
+"""Kernel-level parity (through the C ABI) against torch fp32 references of the same op, with the reference's
+rounding points (fp16(acc+bias) then fp16 add of the residual / time embedding, fp32 norms rounded once).
+Tolerance: rel-L2 <= 2e-3 (observed ~3e-5 for GEMM/conv, 2.5e-4 for attention whose P is rounded to fp16)."""
+import pytest
+import torch
+
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+dev = torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _fp32_refs():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def rnd(g, *s, scale=1.0, shift=0.0):
+    return (torch.randn(*s, generator=g) * scale + shift).half().to(dev)
+
+
+def ref_linear(a, w, bias, addend, rpg):
+    acc = a.float() @ w.float().t()
+    if bias is not None:
+        acc = acc + bias.float()
+    t = acc.half()
+    if addend is not None:
+        ad = addend.float()
+        if rpg > 1:
+            ad = ad.repeat_interleave(rpg, dim=0)[: a.shape[0]]
+        t = (t.float() + ad).half()
+    return t
+
+
+@pytest.mark.parametrize("M,N,K,hb,ha,bn", [
+    (128, 64, 64, False, 0, 64), (256, 256, 256, True, 0, 256), (256, 320, 320, True, 1, 160),
+    (308, 1280, 2048, False, 0, 0), (4096, 1280, 1280, True, 1, 0), (2048, 320, 960, True, 1024, 0),
+    (1000, 200, 192, True, 1, 128), (16384, 1920, 640, False, 0, 0), (1, 64, 64, True, 0, 0), (77, 8, 64, False, 0, 0)])
+def test_linear(M, N, K, hb, ha, bn):
+    from cfgpp_b200 import _native as nv
+    g = torch.Generator().manual_seed(M * 7 + N)
+    a, w = rnd(g, M, K), rnd(g, N, K, scale=K ** -0.5)
+    bias = rnd(g, N) if hb else None
+    addend = rnd(g, M, N) if ha == 1 else (rnd(g, (M + ha - 1) // ha, N) if ha > 1 else None)
+    out = nv.op_linear(a, w, bias, addend, ha if ha > 1 else 1, force_bn=bn)
+    assert rel_l2(out, ref_linear(a, w, bias, addend, ha)) < 2e-3
+
+
+def test_linear_dual_source_and_geglu():
+    from cfgpp_b200 import _native as nv
+    g = torch.Generator().manual_seed(5)
+    a1, a2 = rnd(g, 1024, 640), rnd(g, 1024, 320)
+    w, bias = rnd(g, 320, 960, scale=960 ** -0.5), rnd(g, 320)
+    out = nv.op_linear(a1, w, bias, None, 1, a2=a2)
+    assert rel_l2(out, ref_linear(torch.cat([a1, a2], 1), w, bias, None, 1)) < 2e-3
+    M, Cc = 512, 640
+    inner = 4 * Cc
+    a, w, b = rnd(g, M, Cc), rnd(g, 2 * inner, Cc, scale=Cc ** -0.5), rnd(g, 2 * inner)
+    idx = []
+    for t in range(inner // 128):
+        idx += list(range(t * 128, t * 128 + 128)) + list(range(inner + t * 128, inner + t * 128 + 128))
+    idx = torch.tensor(idx, device=dev)
+    out = nv.op_linear(a, w[idx].contiguous(), b[idx].contiguous(), geglu=True)
+    h = (a.float() @ w.float().t() + b.float()).half()
+    ref = (h[:, :inner].float() * torch.nn.functional.gelu(h[:, inner:].float()).half().float()).half()
+    assert rel_l2(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,ht,hr", [
+    (1, 32, 32, 64, 64, False, False), (2, 64, 64, 128, 128, True, False), (4, 16, 16, 128, 256, False, True),
+    (2, 8, 8, 128, 128, True, False), (1, 128, 128, 320, 320, True, False), (4, 32, 32, 1280, 1280, False, True)])
+def test_conv3x3(B, H, W, Cin, Cout, ht, hr):
+    """Zero padding comes from TMA out-of-bounds fill; edge pixels are therefore the interesting ones."""
+    from cfgpp_b200 import _native as nv
+    g = torch.Generator().manual_seed(H * 3 + Cin)
+    x, w, bias = rnd(g, B, Cin, H, W), rnd(g, Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5), rnd(g, Cout)
+    addend, rpg = None, 1
+    if ht:
+        addend, rpg = rnd(g, B, Cout), H * W
+    elif hr:
+        addend = rnd(g, B * H * W, Cout)
+    out = nv.op_conv3x3(x.permute(0, 2, 3, 1).contiguous(), w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous(),
+                        bias, addend, rpg).reshape(B * H * W, Cout)
+    ref = torch.nn.functional.conv2d(x.float(), w.float(), bias.float(), padding=1).half()
+    ref = ref.permute(0, 2, 3, 1).reshape(B * H * W, Cout)
+    if ht:
+        ref = (ref.float() + addend.float().repeat_interleave(H * W, 0)).half()
+    elif hr:
+        ref = (ref.float() + addend.float()).half()
+    assert rel_l2(out, ref) < 2e-3
+    edge = torch.zeros(B, H, W, dtype=torch.bool, device=dev)
+    edge[:, 0], edge[:, -1], edge[:, :, 0], edge[:, :, -1] = True, True, True, True
+    assert rel_l2(out[edge.reshape(-1)], ref[edge.reshape(-1)]) < 2e-3
+
+
+@pytest.mark.parametrize("B,H,Nq,Nkv", [(1, 1, 128, 128), (1, 4, 64, 64), (2, 5, 1024, 1024), (1, 10, 4096, 4096),
+                                        (4, 20, 1024, 77), (1, 2, 200, 333), (1, 1, 1, 1)])
+def test_attention(B, H, Nq, Nkv):
+    from cfgpp_b200 import _native as nv
+    g = torch.Generator().manual_seed(Nq + Nkv)
+    Cc = H * 64
+    if Nq == Nkv:
+        qkv = rnd(g, B, Nq, 3 * Cc, scale=1.2)
+        q, k, v = qkv[:, :, :Cc], qkv[:, :, Cc:2 * Cc], qkv[:, :, 2 * Cc:]
+    else:
+        q, kv = rnd(g, B, Nq, Cc, scale=1.2), rnd(g, B, Nkv, 2 * Cc, scale=1.2)
+        k, v = kv[:, :, :Cc], kv[:, :, Cc:]
+    out = nv.op_attention(q, k, v, H)
+    qf, kf, vf = (t.float().reshape(B, -1, H, 64).transpose(1, 2) for t in (q, k, v))
+    ref = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B, Nq, Cc)
+    assert rel_l2(out, ref) < 3e-3
+
+
+@pytest.mark.parametrize("B,HW,C1,C2,silu,eps", [(2, 1024, 64, 0, True, 1e-5), (4, 16384, 320, 0, True, 1e-5),
+                                                 (2, 4096, 640, 320, True, 1e-5), (2, 1024, 1280, 640, False, 1e-6)])
+def test_groupnorm(B, HW, C1, C2, silu, eps):
+    from cfgpp_b200 import _native as nv
+    g = torch.Generator().manual_seed(C1 + C2)
+    x1 = rnd(g, B, HW, C1, scale=2.0, shift=0.5)
+    x2 = rnd(g, B, HW, C2, scale=0.7, shift=-0.3) if C2 else None
+    Cc = C1 + C2
+    gamma, beta = rnd(g, Cc, scale=0.2, shift=1.0), rnd(g, Cc, scale=0.2)
+    out = nv.op_groupnorm(x1, gamma, beta, eps, silu, x2)
+    x = torch.cat([x1, x2], 2) if C2 else x1
+    ref = torch.nn.functional.group_norm(x.float().permute(0, 2, 1).reshape(B, Cc, HW, 1), 32, gamma.float(),
+                                         beta.float(), eps)
+    if silu:
+        ref = torch.nn.functional.silu(ref)
+    assert rel_l2(out, ref.reshape(B, Cc, HW).permute(0, 2, 1).half()) < 1e-3
+
+
+@pytest.mark.parametrize("M,Cc", [(4096, 1280), (16384, 640), (300, 128)])
+def test_layernorm(M, Cc):
+    from cfgpp_b200 import _native as nv
+    g = torch.Generator().manual_seed(M)
+    x, gamma, beta = rnd(g, M, Cc, scale=3.0, shift=1.0), rnd(g, Cc, scale=0.2, shift=1.0), rnd(g, Cc, scale=0.2)
+    ref = torch.nn.functional.layer_norm(x.float(), (Cc,), gamma.float(), beta.float(), 1e-5).half()
+    assert rel_l2(nv.op_layernorm(x, gamma, beta), ref) < 1e-3
