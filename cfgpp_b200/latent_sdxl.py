@@ -324,7 +324,8 @@ class BaseDDIMCFGpp(SDXL):
         zt = kwargs.get('zT')
         if zt is None:
             zt = self.initialize_latent(size=(b, 4, shape[1] // self.vae_scale_factor, shape[0] // self.vae_scale_factor))
-        steps = S.ddim_cfgpp_steps(self._sch, cfg_guidance, sdxl_indexing=True)
+        steps = S.ddim_cfgpp_steps(self._sch, cfg_guidance, sdxl_indexing=True,
+                                   tables_on_device=(self.schedule_kind == "lightning"))
         # fp32 state: zt comes from torch.randn (fp32) and promotes every update (latent_sdxl.py:289, 741-744)
         return self._run_trajectory(S.STEP_DDIM_CFGPP, torch.float32, steps, zt.float(), null_prompt_embeds,
                                     prompt_embeds, add_cond_kwargs, callback_fn, 'z0t')

@@ -86,17 +86,23 @@ def _state(t: float, in_scale: float, lam: float, c=(0, 0, 0, 0), d=(0, 0, 0, 0)
     return s
 
 
-def ddim_cfgpp_steps(sch: Schedule, cfg_guidance: float, sdxl_indexing: bool) -> List[StepStateC]:
+def ddim_cfgpp_steps(sch: Schedule, cfg_guidance: float, sdxl_indexing: bool,
+                     tables_on_device: bool = False) -> List[StepStateC]:
     """Sampling loop scalars. sdxl_indexing: `alphas_cumprod[t - skip]` with Python negative-index wrap on the last
-    step (latent_sdxl.py:732-734); otherwise StableDiffusion.alpha() (negative -> final_alpha_cumprod)."""
+    step (latent_sdxl.py:732-734); otherwise StableDiffusion.alpha() (negative -> final_alpha_cumprod).
+    tables_on_device (Lightning, latent_sdxl.py:418): the table is a CUDA tensor there, and PyTorch casts a 0-dim
+    CUDA operand of an fp16 tensor op to fp16 first — so the two scalars that multiply the fp16 eps tensors are
+    rounded through fp16 (a CPU 0-dim operand, the SDXL / SD1.5 case, enters as an fp32 scalar instead)."""
     out = []
     for t in sch.timesteps.int():
         if sdxl_indexing:
             at, at_next = sch.alphas_cumprod[t], sch.alphas_cumprod[t - sch.skip]
         else:
             at, at_next = sch.alpha(t), sch.alpha(t - sch.skip)
-        out.append(_state(float(t), 1.0, cfg_guidance,
-                          c=((1 - at).sqrt(), at.sqrt(), at_next.sqrt(), (1 - at_next).sqrt())))
+        c0, c3 = (1 - at).sqrt(), (1 - at_next).sqrt()
+        if tables_on_device:
+            c0, c3 = c0.half().float(), c3.half().float()
+        out.append(_state(float(t), 1.0, cfg_guidance, c=(c0, at.sqrt(), at_next.sqrt(), c3)))
     return out
 
 

@@ -61,8 +61,8 @@ def sd15_ddim_cfgpp(unet, tb: ScheduleTables, zT, uc, c, cfg_guidance: float,
     zt = zT
     z0t = None
     for step, t in enumerate(tb.timesteps):
-        at = _alpha_sd15(tb, t).to(zt.device)
-        at_prev = _alpha_sd15(tb, t - tb.skip).to(zt.device)
+        at = _alpha_sd15(tb, t)            # CPU 0-dim tensor, as in the reference (acts as an fp32 scalar)
+        at_prev = _alpha_sd15(tb, t - tb.skip)
         noise_uc, noise_c = predict_noise(unet, zt, t.to(zt.device), uc, c)
         noise_pred = noise_uc + cfg_guidance * (noise_c - noise_uc)
         if record is not None:
@@ -80,8 +80,8 @@ def sd15_inversion_cfgpp(unet, tb: ScheduleTables, z0, uc, c, cfg_guidance: floa
     """InversionDDIMCFGpp.inversion, latent_diffusion.py:888-910 (Tweedie with eps_uc, renoise with guided eps)."""
     zt = z0.clone()
     for t in reversed(tb.timesteps):
-        at = _alpha_sd15(tb, t).to(zt.device)
-        at_prev = _alpha_sd15(tb, t - tb.skip).to(zt.device)
+        at = _alpha_sd15(tb, t)
+        at_prev = _alpha_sd15(tb, t - tb.skip)
         noise_uc, noise_c = predict_noise(unet, zt, t.to(zt.device), uc, c)
         noise_pred = noise_uc + cfg_guidance * (noise_c - noise_uc)
         z0t = (zt - (1 - at_prev).sqrt() * noise_uc) / at_prev.sqrt()
@@ -98,16 +98,19 @@ def sd15_ddim_inversion_cfgpp(unet, tb, z0_src, uc, c, cfg_guidance, callback_fn
 
 @torch.no_grad()
 def sdxl_ddim_cfgpp(unet, tb: ScheduleTables, zT, uc, c, cfg_guidance: float, add_cond_kwargs,
-                    callback_fn: Optional[Callable] = None, record: Optional[list] = None):
+                    callback_fn: Optional[Callable] = None, record: Optional[list] = None,
+                    tables_on_device: bool = False):
     """BaseDDIMCFGpp.reverse_process, latent_sdxl.py:715-755. `at_next` of the last step is a negative-index
-    lookup (t - skip < 0) whose result only feeds the discarded last zt (Appendix C.2)."""
+    lookup (t - skip < 0) whose result only feeds the discarded last zt (Appendix C.2).
+    The table lives on the CPU for SDXL (:67) — a CPU 0-dim operand enters CUDA tensor ops as an fp32 scalar — and
+    on the device for Lightning (:418), where a 0-dim CUDA operand of an fp16 tensor op is first cast to fp16."""
     zt = zT
     z0t = None
-    acp = tb.alphas_cumprod
+    acp = tb.alphas_cumprod.to(zt.device) if tables_on_device else tb.alphas_cumprod
     for step, t in enumerate(tb.timesteps.int()):
         next_t = t - tb.skip
-        at = acp[t].to(zt.device)
-        at_next = acp[next_t].to(zt.device)
+        at = acp[t]
+        at_next = acp[next_t]
         noise_uc, noise_c = predict_noise(unet, zt, t.to(zt.device), uc, c, add_cond_kwargs)
         noise_pred = noise_uc + cfg_guidance * (noise_c - noise_uc)
         if record is not None:
@@ -124,7 +127,8 @@ def sdxl_ddim_cfgpp(unet, tb: ScheduleTables, zT, uc, c, cfg_guidance: float, ad
 def sdxl_ddim_cfgpp_lightning(unet, tb, zT, uc, c, cfg_guidance, add_cond_kwargs, callback_fn=None, record=None):
     """BaseDDIMCFGppLight.reverse_process, latent_sdxl.py:843-858."""
     assert cfg_guidance == 1.0, "CFG should be turned off in the lightning version"
-    return sdxl_ddim_cfgpp(unet, tb, zT, uc, c, cfg_guidance, add_cond_kwargs, callback_fn, record)
+    return sdxl_ddim_cfgpp(unet, tb, zT, uc, c, cfg_guidance, add_cond_kwargs, callback_fn, record,
+                           tables_on_device=True)
 
 
 def sigma_to_t(tb: ScheduleTables, sigma: torch.Tensor) -> torch.Tensor:

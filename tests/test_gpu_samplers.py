@@ -31,7 +31,7 @@ def test_step_kernel_ddim_matches_reference_arithmetic():
         eu = torch.randn(2, 4, 32, 32, generator=g).half().to(dev)
         ec = torch.randn(2, 4, 32, 32, generator=g).half().to(dev)
         t = int(st.t)
-        at, an = sch.alphas_cumprod[t].to(dev), sch.alphas_cumprod[t - sch.skip].to(dev)
+        at, an = sch.alphas_cumprod[t], sch.alphas_cumprod[t - sch.skip]  # CPU 0-dim tensors, as in the reference
         npred = eu + 0.6 * (ec - eu)                             # latent_sdxl.py:738 (fp16 tensor ops)
         z0_ref = (zt - (1 - at).sqrt() * npred) / at.sqrt()      # :741
         zn_ref = an.sqrt() * z0_ref + (1 - an).sqrt() * eu       # :744
@@ -43,7 +43,7 @@ def test_step_kernel_ddim_matches_reference_arithmetic():
     # inversion: Tweedie with eps_uc, renoise with the guided eps (latent_diffusion.py:907-908), fp16 state
     inv = S.ddim_inversion_cfgpp_steps(sch, 0.6)[5]
     t = int(inv.t)
-    at, ap = sch.alpha(t).to(dev), sch.alpha(t - sch.skip).to(dev)
+    at, ap = sch.alpha(t), sch.alpha(t - sch.skip)
     zt = torch.randn(1, 4, 32, 32, generator=g).half().to(dev)
     eu = torch.randn(1, 4, 32, 32, generator=g).half().to(dev)
     ec = torch.randn(1, 4, 32, 32, generator=g).half().to(dev)
