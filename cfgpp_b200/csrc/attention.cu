@@ -1,30 +1,38 @@
 // cfgpp_b200 — flash-style attention forward for head_dim 64 on tcgen05/TMEM (sm_100a). See attention.cuh.
 //
-// One CTA = 128 query rows of one (batch, head); loop over 128-wide KV tiles.
-//   warp 0 lane 0 : TMA producer (Q once; K/V rings, 128B swizzle)
-//   warp 1 lane 0 : MMA issuer   S_b = Q K_j^T  (M128 N128 K64 -> TMEM, double-buffered b = j&1)
-//                                O_t = P_j V_j  (M128 N64 K128, A = P from smem, B = V MN-major)
-//   warp 2        : TMEM allocator (512 columns: S0 [0,128) S1 [128,256) O_t [256,320))
-//   warps 4..7    : softmax, one query row per thread: online max / exp2 / running sum in fp32, P rounded to
-//                   fp16 into swizzled smem (the SS-operand of the PV MMA), O accumulated in registers with the
-//                   usual exp2((m_old - m_new) c) rescale, final 1/l normalisation and fp16 store.
-// QK_{j+1} is issued before PV_j so the tensor pipe works on the next scores while the softmax warps are busy.
+// One CTA = up to two 128-row query tiles of one (batch, head) ("ping-pong"), looping over 128-wide KV tiles that
+// both query tiles share (K / V are fetched once per pair):
+//   warp 0 lane 0 : TMA producer (Q0, Q1 once; K / V rings, 128B swizzle)
+//   warp 1 lane 0 : MMA issuer   S_q = Q_q K_j^T   (M128 N128 K64, fp32 in TMEM)
+//                                O_q += P_q V_j    (M128 N64 K128; A = P from swizzled smem, B = V MN-major),
+//                   interleaved  PV_0(j) QK_0(j+1) PV_1(j) QK_1(j+1)  so the tensor pipe works for one query tile
+//                   while the softmax warps of the other are busy
+//   warp 2        : TMEM allocator (512 columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384))
+//   warps 4..7    : softmax of query tile 0, warps 8..11: query tile 1 — one row per thread:
+//                   a single TMEM read of the 128 scores into registers, row max, p = exp2((s - m) * scale*log2e),
+//                   fp32 row sum, P rounded to fp16 into smem. O accumulates in TMEM across KV tiles; the running
+//                   max is only advanced (and O / l rescaled, through tcgen05.ld/st) when the new maximum exceeds
+//                   the reference by more than 2^8 in the exp2 domain — exact after the final 1/l normalisation,
+//                   and p <= 256 stays well inside fp16 / fp32 range.
 #include "attention.cuh"
 #include "common.cuh"
 
 namespace cfgpp {
+
+void attn_configure();
 
 namespace {
 
 constexpr int BQ = 128;
 constexpr int BKV = 128;
 constexpr int HD = 64;
-constexpr int KS = 3;  // K / V ring depth
-constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KB: Q, K, V tiles and each of the two P sub-tiles
-constexpr int SMEM_BYTES = TILE_BYTES * (1 + 2 * KS + 2) + 1024 + 256;
-constexpr int kThreads = 256;
+constexpr int KS = 3;                     // K / V ring depth
+constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KB: Q, K, V tiles and each 64-column half of a P tile
+constexpr int SMEM_BYTES = TILE_BYTES * (2 + 2 * KS + 4) + 1024 + 256;
+constexpr int kThreads = 384;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t O_COL = 256;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 __global__ void __launch_bounds__(kThreads, 1)
 attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
@@ -32,28 +40,28 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + TILE_BYTES;
-  uint8_t* sV = sK + KS * TILE_BYTES;
-  uint8_t* sP = sV + KS * TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * TILE_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;
+  uint8_t* sQ = smem;                      // 2 tiles
+  uint8_t* sK = sQ + 2 * TILE_BYTES;       // KS tiles
+  uint8_t* sV = sK + KS * TILE_BYTES;      // KS tiles
+  uint8_t* sP = sV + KS * TILE_BYTES;      // 2 query tiles x 2 halves
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * TILE_BYTES);
+  uint64_t* q_full = bars;            // [2]
+  uint64_t* k_full = q_full + 2;      // [KS]
   uint64_t* k_empty = k_full + KS;
   uint64_t* v_full = k_empty + KS;
   uint64_t* v_empty = v_full + KS;
-  uint64_t* s_full = v_empty + KS;
-  uint64_t* s_empty = s_full + 2;
-  uint64_t* p_full = s_empty + 2;
-  uint64_t* pv_done = p_full + 1;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pv_done + 1);
+  uint64_t* s_full = v_empty + KS;    // [2]
+  uint64_t* p_full = s_full + 2;      // [2]
+  uint64_t* pv_done = p_full + 2;     // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BQ;
+  const int q0 = blockIdx.x * 2 * BQ;
   const int head = blockIdx.y;
   const int batch = blockIdx.z;
   const int n_tiles = (p.Nkv + BKV - 1) / BKV;
+  const int n_qt = (q0 + BQ < p.Nq) ? 2 : 1;  // query tiles handled by this CTA
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&map_q);
@@ -61,19 +69,18 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
     tma_prefetch_desc(&map_v);
   }
   if (warp_idx == 1 && lane == 0) {
-    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&pv_done[i], 1);
+    }
     for (int i = 0; i < KS; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 128);
-    }
-    mbar_init(p_full, 128);
-    mbar_init(pv_done, 1);
     fence_barrier_init();
   }
   if (warp_idx == 2) {
@@ -88,8 +95,10 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
   if (warp_idx == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
-      mbar_arrive_expect_tx(q_full, TILE_BYTES);
-      tma_load_3d(sQ, &map_q, q_full, head * HD, q0, batch);
+      for (int qt = 0; qt < n_qt; ++qt) {
+        mbar_arrive_expect_tx(&q_full[qt], TILE_BYTES);
+        tma_load_3d(sQ + qt * TILE_BYTES, &map_q, &q_full[qt], head * HD, q0 + qt * BQ, batch);
+      }
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j % KS;
         const uint32_t ph = (j / KS) & 1;
@@ -106,134 +115,149 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc_qk = make_idesc_f16(128, BKV, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_f16(128, HD, 0, 1);  // B (= V) is MN-major
-      const uint64_t q_desc = make_sdesc_sw128(smem_u32(sQ), 1024, 0);
-      auto issue_qk = [&](int j) {
-        const int s = j % KS;
-        const int b = j & 1;
-        mbar_wait(&k_full[s], (j / KS) & 1);
-        mbar_wait(&s_empty[b], ((j >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint64_t k_desc = make_sdesc_sw128(smem_u32(sK + s * TILE_BYTES), 1024, 0);
+      auto issue_qk = [&](int qt, int j) {
+        const uint64_t q_desc = make_sdesc_sw128(smem_u32(sQ + qt * TILE_BYTES), 1024, 0);
+        const uint64_t k_desc = make_sdesc_sw128(smem_u32(sK + (j % KS) * TILE_BYTES), 1024, 0);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          umma_f16(tmem_base + b * BKV, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
-        umma_commit(&k_empty[s]);
-        umma_commit(&s_full[b]);
+          umma_f16(tmem_base + qt * BKV, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[qt]);
       };
-      mbar_wait(q_full, 0);
-      issue_qk(0);
-      for (int j = 0; j < n_tiles; ++j) {
-        if (j + 1 < n_tiles) issue_qk(j + 1);
-        const int s = j % KS;
-        mbar_wait(&v_full[s], (j / KS) & 1);
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
+      auto issue_pv = [&](int qt, int j) {
         // V tile: 128 kv rows x 64 d (128 B per row, swizzled) = MN-major B operand with a single 64-wide MN atom:
         // 8-row K groups are 1024 B apart (SBO); a K step of 16 rows advances 2048 B.
-        const uint64_t v_desc = make_sdesc_sw128(smem_u32(sV + s * TILE_BYTES), 1024, TILE_BYTES);
+        const uint64_t v_desc = make_sdesc_sw128(smem_u32(sV + (j % KS) * TILE_BYTES), 1024, TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
-          const uint64_t p_desc = make_sdesc_sw128(smem_u32(sP + (k >> 2) * TILE_BYTES), 1024, 0) + 2 * (k & 3);
-          umma_f16(tmem_base + O_COL, p_desc, v_desc + 128 * k, idesc_pv, k != 0 ? 1u : 0u);
+          const uint64_t p_desc =
+              make_sdesc_sw128(smem_u32(sP + (2 * qt + (k >> 2)) * TILE_BYTES), 1024, 0) + 2 * (k & 3);
+          umma_f16(tmem_base + O_COL + qt * HD, p_desc, v_desc + 128 * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&v_empty[s]);
-        umma_commit(pv_done);
+        umma_commit(&pv_done[qt]);
+      };
+      for (int qt = 0; qt < n_qt; ++qt) mbar_wait(&q_full[qt], 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      for (int qt = 0; qt < n_qt; ++qt) issue_qk(qt, 0);
+      umma_commit(&k_empty[0]);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int sv = j % KS;
+        mbar_wait(&v_full[sv], (j / KS) & 1);
+        const bool more = (j + 1 < n_tiles);
+        if (more) mbar_wait(&k_full[(j + 1) % KS], ((j + 1) / KS) & 1);
+        for (int qt = 0; qt < n_qt; ++qt) {
+          mbar_wait(&p_full[qt], j & 1);  // P_q(j) written (implies S_q(j) consumed and any O_q rescale finished)
+          tc_fence_after();
+          issue_pv(qt, j);
+          if (more) issue_qk(qt, j + 1);
+        }
+        umma_commit(&v_empty[sv]);
+        if (more) umma_commit(&k_empty[(j + 1) % KS]);
       }
     }
   } else if (warp_idx >= 4) {
     // ===================== softmax / output =====================
-    const int qw = warp_idx - 4;
-    const int row = qw * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(qw * 32) << 16;
-    const float c = p.scale_log2e;
-    float m_run = -INFINITY, l_run = 0.f, alpha_pending = 0.f;
-    float o_acc[HD];
-#pragma unroll
-    for (int d = 0; d < HD; ++d) o_acc[d] = 0.f;
+    const int qt = (warp_idx - 4) >> 2;
+    if (qt < n_qt) {
+      const int qw = warp_idx & 3;  // TMEM lane quarter of this warp
+      const int row = qw * 32 + lane;
+      const uint32_t lane_off = static_cast<uint32_t>(qw * 32) << 16;
+      const uint32_t s_addr = tmem_base + qt * BKV + lane_off;
+      const uint32_t o_addr = tmem_base + O_COL + qt * HD + lane_off;
+      uint8_t* prow = sP + 2 * qt * TILE_BYTES + row * 128;
+      const float c = p.scale_log2e;
+      float m_ref = -INFINITY, l_run = 0.f;
 
-    auto fold_o = [&]() {  // o_acc = o_acc * alpha_pending + O_t
+      for (int j = 0; j < n_tiles; ++j) {
+        const int valid = p.Nkv - j * BKV;  // columns >= valid are padding (last tile only)
+        mbar_wait(&s_full[qt], j & 1);
+        tc_fence_after();
+        uint32_t s[128];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) tmem_ld_x32(s_addr + g * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[g * 32]));
+        tmem_ld_wait();
+        if (valid < BKV) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (i >= valid) s[i] = 0xff800000u;  // -inf
+        }
+        float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
+#pragma unroll
+        for (int i = 2; i < 128; i += 2) {
+          mx0 = fmaxf(mx0, __uint_as_float(s[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+        }
+        const float mx = fmaxf(mx0, mx1);
+        // lazy running max: move the reference only when it would otherwise overflow the comfortable range
+        float alpha = 1.0f;
+        bool need = false;
+        if (j == 0) {
+          m_ref = mx;
+        } else if ((mx - m_ref) * c > kRescaleThreshold) {
+          alpha = fast_exp2((m_ref - mx) * c);
+          m_ref = mx;
+          need = true;
+        }
+        if (j > 0) {
+          mbar_wait(&pv_done[qt], (j - 1) & 1);  // PV_q(j-1) retired: P buffer reusable, O_q rescalable
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, need)) {
+#pragma unroll 1
+            for (int h = 0; h < 4; ++h) {  // 16 columns at a time: the 128 scores stay live in registers
+              uint32_t o[16];
+              tmem_ld_x16(o_addr + h * 16, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int d = 0; d < 16; ++d) o[d] = __float_as_uint(__uint_as_float(o[d]) * alpha);
+              tmem_st_x16(o_addr + h * 16, o);
+            }
+            tmem_st_wait();
+            l_run *= alpha;
+          }
+        }
+        const float mc = m_ref * c;
+        float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {  // 16-byte chunks of the 256-byte P row (two 128-byte halves)
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float p0 = fast_exp2(__uint_as_float(s[g * 8 + 2 * e]) * c - mc);
+            const float p1 = fast_exp2(__uint_as_float(s[g * 8 + 2 * e + 1]) * c - mc);
+            rs0 += p0;
+            rs1 += p1;
+            pk[e] = pack_half2(p0, p1);
+          }
+          const int half_idx = g >> 3;        // which 64-column half
+          const int ch = (g & 7) ^ (row & 7);  // 128B swizzle
+          *reinterpret_cast<uint4*>(prow + half_idx * TILE_BYTES + ch * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        l_run += rs0 + rs1;
+        tc_fence_before();
+        fence_proxy_async_smem();
+        mbar_arrive(&p_full[qt]);
+      }
+      mbar_wait(&pv_done[qt], (n_tiles - 1) & 1);
+      tc_fence_after();
+      const float inv_l = 1.0f / l_run;
+      const int qrow = q0 + qt * BQ + row;
+      __half* dst = p.out + (static_cast<size_t>(batch) * p.Nq + qrow) * p.ldo + head * HD;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        uint32_t v[32];
-        tmem_ld_x32(tmem_base + O_COL + h * 32 + lane_off, v);
+        uint32_t o[32];
+        tmem_ld_x32(o_addr + h * 32, o);
         tmem_ld_wait();
+        if (qrow < p.Nq) {
 #pragma unroll
-        for (int d = 0; d < 32; ++d) o_acc[h * 32 + d] = o_acc[h * 32 + d] * alpha_pending + __uint_as_float(v[d]);
-      }
-    };
-
-    for (int j = 0; j < n_tiles; ++j) {
-      const int b = j & 1;
-      const int valid = p.Nkv - j * BKV;  // columns >= valid are padding
-      mbar_wait(&s_full[b], (j >> 1) & 1);
-      tc_fence_after();
-      const uint32_t s_addr = tmem_base + b * BKV + lane_off;
-      // pass A: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BKV; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_x32(s_addr + c0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = (c0 + i < valid) ? __uint_as_float(v[i]) : -INFINITY;
-          mx = fmaxf(mx, s);
+          for (int i = 0; i < 4; ++i) {
+            uint4 w;
+            w.x = pack_half2(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
+            w.y = pack_half2(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
+            w.z = pack_half2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
+            w.w = pack_half2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
+            reinterpret_cast<uint4*>(dst + h * 32)[i] = w;
+          }
         }
-      }
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = exp2f((m_run - m_new) * c);
-      const float mc = m_new * c;
-      if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);  // PV_{j-1} retired: O_t readable, P buffer reusable
-        tc_fence_after();
-        fold_o();
-      }
-      // pass B: p = exp2(s c - m c); row sum; fp16 P into the swizzled K-major A tile(s)
-      float rs = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BKV; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_x32(s_addr + c0, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = (c0 + 2 * i < valid) ? fast_exp2(__uint_as_float(v[2 * i]) * c - mc) : 0.f;
-          float p1 = (c0 + 2 * i + 1 < valid) ? fast_exp2(__uint_as_float(v[2 * i + 1]) * c - mc) : 0.f;
-          rs += p0 + p1;
-          pk[i] = pack_half2(p0, p1);
-        }
-        uint8_t* prow = sP + (c0 >> 6) * TILE_BYTES + row * 128;
-        const int chunk0 = (c0 & 63) >> 3;  // first 16-byte chunk of this 32-column group within the 128 B row
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int ch = (chunk0 + i) ^ (row & 7);
-          *reinterpret_cast<uint4*>(prow + ch * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(&s_empty[b]);
-      fence_proxy_async_smem();
-      mbar_arrive(p_full);
-      l_run = l_run * alpha + rs;
-      alpha_pending = alpha;
-      m_run = m_new;
-    }
-    mbar_wait(pv_done, (n_tiles - 1) & 1);
-    tc_fence_after();
-    fold_o();
-    const float inv_l = 1.0f / l_run;
-    if (q0 + row < p.Nq) {
-      __half* dst = p.out + (static_cast<size_t>(batch) * p.Nq + q0 + row) * p.ldo + head * HD;
-#pragma unroll
-      for (int i = 0; i < HD / 8; ++i) {
-        uint4 o;
-        o.x = pack_half2(o_acc[8 * i + 0] * inv_l, o_acc[8 * i + 1] * inv_l);
-        o.y = pack_half2(o_acc[8 * i + 2] * inv_l, o_acc[8 * i + 3] * inv_l);
-        o.z = pack_half2(o_acc[8 * i + 4] * inv_l, o_acc[8 * i + 5] * inv_l);
-        o.w = pack_half2(o_acc[8 * i + 6] * inv_l, o_acc[8 * i + 7] * inv_l);
-        reinterpret_cast<uint4*>(dst)[i] = o;
       }
     }
   }
@@ -277,7 +301,7 @@ void attn_configure() {
 
 void run_attn_op(const AttnOp& op, cudaStream_t stream) {
   attn_configure();
-  dim3 grid((op.p.Nq + BQ - 1) / BQ, op.p.H, op.p.B);
+  dim3 grid((op.p.Nq + 2 * BQ - 1) / (2 * BQ), op.p.H, op.p.B);
   attn_kernel<<<grid, kThreads, SMEM_BYTES, stream>>>(op.p, op.map_q, op.map_k, op.map_v);
   CFGPP_CHECK_CUDA(cudaGetLastError());
 }

@@ -20,32 +20,41 @@ constexpr int BK = 64;
 constexpr int kThreads = 256;
 constexpr int A_BYTES = BM * BK * 2;
 
-template <int BN>
+template <int BN, bool GEGLU>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN >= 160 ? 5 : 6);
+  // output columns of a tile and its smem staging area: OUT_N / 32 sub-tiles of [128 rows x 64 B], 64B swizzle
+  static constexpr int OUT_N = GEGLU ? BN / 2 : BN;
+  static constexpr int EPI_SUB = OUT_N / 32;
+  static constexpr int EPI_SUB_BYTES = BM * 64;
+  static constexpr int EPI_BYTES = EPI_SUB * EPI_SUB_BYTES;
+  static constexpr int STAGES = GEGLU ? 4 : (BN == 256 ? 3 : (BN == 160 ? 5 : 6));
   static constexpr int TMEM_COLS = (BN <= 64) ? 128 : (BN <= 128 ? 256 : 512);
   static constexpr int ACC_STRIDE = TMEM_COLS / 2;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of an SM");
 };
 
 template <int BN, bool GEGLU>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
-            const __grid_constant__ CUtensorMap map_b) {
-  using C = Cfg<BN>;
+            const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
+            const __grid_constant__ CUtensorMap map_res) {
+  using C = Cfg<BN, GEGLU>;
   extern __shared__ uint8_t smem_raw[];
   // 1024B alignment (required by the 128B swizzle atoms) in the shared address space
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* epi_smem = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + C::EPI_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::STAGES;
   uint64_t* tmem_full_bar = bars + 2 * C::STAGES;
   uint64_t* tmem_empty_bar = bars + 2 * C::STAGES + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  uint64_t* res_full_bar = bars + 2 * C::STAGES + 4;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 5);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -54,6 +63,8 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_a2);
     tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&map_out);
+    tma_prefetch_desc(&map_res);
   }
   if (warp_idx == 1 && lane == 0) {
     for (int i = 0; i < C::STAGES; ++i) {
@@ -64,6 +75,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], 128);
     }
+    mbar_init(res_full_bar, 1);
     fence_barrier_init();
   }
   if (warp_idx == 2) {
@@ -156,9 +168,25 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
     }
   } else if (warp_idx >= 4) {
     // ===================== epilogue =====================
+    // TMEM -> registers -> (bias / time-embedding row / residual / GEGLU) -> fp16 into the swizzled smem staging
+    // tile -> TMA store (coalesced, clipped at the M / N edges by the hardware). The full residual tile is TMA-loaded
+    // into the same staging area while the main loop of the tile runs, and overwritten in place.
     const int q = warp_idx - 4;  // == warp_idx % 4: the TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const bool leader = (threadIdx.x == 128);
+    const bool full_res = (p.addend != nullptr) && (p.add_rows_per_group <= 1);
+    const int sw = (row >> 1) & 3;  // 64B swizzle: 16-byte chunk index ^= (row / 2) % 4
+    uint8_t* my_row = epi_smem + row * 64;
+    auto issue_residual = [&](int tile) {
+      const int m_blk = tile % p.num_m_blocks;
+      const int n_blk = tile / p.num_m_blocks;
+      mbar_arrive_expect_tx(res_full_bar, C::EPI_BYTES);
+#pragma unroll 1
+      for (int j = 0; j < C::EPI_SUB; ++j)
+        tma_load_2d(epi_smem + j * C::EPI_SUB_BYTES, &map_res, res_full_bar, n_blk * C::OUT_N + j * 32, m_blk * BM);
+    };
+    if (full_res && leader && static_cast<int>(blockIdx.x) < num_tiles) issue_residual(blockIdx.x);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -168,91 +196,114 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
       const int m = m_blk * BM + row;
       mbar_wait(&tmem_full_bar[as], aph);
       tc_fence_after();
+      if (full_res) mbar_wait(res_full_bar, it & 1);
       const uint32_t t_base = tmem_base + as * C::ACC_STRIDE + lane_off;
-      const __half* add_row = nullptr;
-      if (p.addend != nullptr && m < p.M)
-        add_row = p.addend + static_cast<size_t>(p.add_rows_per_group > 1 ? m / p.add_rows_per_group : m) * p.ld_add;
+      const __half* add_row = nullptr;  // per-sample row broadcast (ResnetBlock2D time embedding)
+      if (p.addend != nullptr && !full_res) {
+        const int mm = m < p.M ? m : p.M - 1;
+        add_row = p.addend + static_cast<size_t>(mm / p.add_rows_per_group) * p.ld_add;
+      }
 
       if constexpr (!GEGLU) {
-        __half* out_row = p.out + static_cast<size_t>(m) * p.ldc;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int j = 0; j < C::EPI_SUB; ++j) {
           uint32_t v[32];
-          tmem_ld_x32(t_base + c0, v);
+          tmem_ld_x32(t_base + j * 32, v);
           tmem_ld_wait();
-          const int n0 = n_blk * BN + c0;
-          if (m < p.M && n0 < p.N) {
-            if (n0 + 32 <= p.N) {
-              uint32_t o[16];
+          const int n0 = n_blk * BN + j * 32;
+          uint8_t* srow = my_row + j * C::EPI_SUB_BYTES;
+          const bool cols_ok = (n0 + 32 <= p.N);
+          uint32_t o[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
-                if (p.bias) {
-                  const __half2 b = *reinterpret_cast<const __half2*>(p.bias + n0 + 2 * j);
+          for (int c = 0; c < 4; ++c) {
+            uint4 r4 = make_uint4(0, 0, 0, 0);
+            if (full_res) r4 = *reinterpret_cast<const uint4*>(srow + ((c ^ sw) << 4));
+            const __half2* rh = reinterpret_cast<const __half2*>(&r4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int jj = c * 4 + e;  // half2 index within the 32-column chunk
+              float x0 = __uint_as_float(v[2 * jj]), x1 = __uint_as_float(v[2 * jj + 1]);
+              if (p.bias) {
+                if (cols_ok) {
+                  const __half2 b = *reinterpret_cast<const __half2*>(p.bias + n0 + 2 * jj);
                   x0 += __low2float(b);
                   x1 += __high2float(b);
+                } else {
+                  if (n0 + 2 * jj < p.N) x0 += __half2float(p.bias[n0 + 2 * jj]);
+                  if (n0 + 2 * jj + 1 < p.N) x1 += __half2float(p.bias[n0 + 2 * jj + 1]);
                 }
-                __half2 t = __floats2half2_rn(x0, x1);
-                if (add_row) {
-                  const __half2 a = *reinterpret_cast<const __half2*>(add_row + n0 + 2 * j);
-                  t = __floats2half2_rn(__low2float(t) + __low2float(a), __high2float(t) + __high2float(a));
+              }
+              __half2 t = __floats2half2_rn(x0, x1);
+              if (full_res) {
+                t = __floats2half2_rn(__low2float(t) + __low2float(rh[e]), __high2float(t) + __high2float(rh[e]));
+              } else if (add_row) {
+                float a0 = 0.f, a1 = 0.f;
+                if (cols_ok) {
+                  const __half2 a = *reinterpret_cast<const __half2*>(add_row + n0 + 2 * jj);
+                  a0 = __low2float(a);
+                  a1 = __high2float(a);
+                } else {
+                  if (n0 + 2 * jj < p.N) a0 = __half2float(add_row[n0 + 2 * jj]);
+                  if (n0 + 2 * jj + 1 < p.N) a1 = __half2float(add_row[n0 + 2 * jj + 1]);
                 }
-                o[j] = *reinterpret_cast<uint32_t*>(&t);
+                t = __floats2half2_rn(__low2float(t) + a0, __high2float(t) + a1);
               }
-              uint4* dst = reinterpret_cast<uint4*>(out_row + n0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-            } else {
-              for (int j = 0; j < 32 && n0 + j < p.N; ++j) {
-                float x = __uint_as_float(v[j]);
-                if (p.bias) x += __half2float(p.bias[n0 + j]);
-                __half t = __float2half_rn(x);
-                if (add_row) t = __float2half_rn(__half2float(t) + __half2float(add_row[n0 + j]));
-                out_row[n0 + j] = t;
-              }
+              o[jj] = *reinterpret_cast<uint32_t*>(&t);
             }
+            *reinterpret_cast<uint4*>(srow + ((c ^ sw) << 4)) = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
           }
         }
       } else {
         // value columns [0,128), gate columns [128,256) of this tile -> 128 output columns
-        __half* out_row = p.out + static_cast<size_t>(m) * p.ldc + n_blk * (BN / 2);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+        for (int j = 0; j < C::EPI_SUB; ++j) {
           uint32_t va[32], vg[32];
-          tmem_ld_x32(t_base + c0, va);
-          tmem_ld_x32(t_base + BN / 2 + c0, vg);
+          tmem_ld_x32(t_base + j * 32, va);
+          tmem_ld_x32(t_base + BN / 2 + j * 32, vg);
           tmem_ld_wait();
-          if (m < p.M) {
-            const int na = n_blk * BN + c0;  // packed-row index of the value half (bias is packed alike)
-            const int ng = na + BN / 2;
-            uint32_t o[16];
+          const int na = n_blk * BN + j * 32;  // packed-row index of the value half (bias is packed alike)
+          const int ng = na + BN / 2;
+          uint8_t* srow = my_row + j * C::EPI_SUB_BYTES;
+          uint32_t o[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float a0 = __uint_as_float(va[2 * j]), a1 = __uint_as_float(va[2 * j + 1]);
-              float g0 = __uint_as_float(vg[2 * j]), g1 = __uint_as_float(vg[2 * j + 1]);
-              if (p.bias) {
-                const __half2 ba = *reinterpret_cast<const __half2*>(p.bias + na + 2 * j);
-                const __half2 bg = *reinterpret_cast<const __half2*>(p.bias + ng + 2 * j);
-                a0 += __low2float(ba);
-                a1 += __high2float(ba);
-                g0 += __low2float(bg);
-                g1 += __high2float(bg);
-              }
-              const __half2 ah = __floats2half2_rn(a0, a1);
-              const __half2 gh = __floats2half2_rn(g0, g1);
-              const __half2 ge = __floats2half2_rn(gelu_erf_f(__low2float(gh)), gelu_erf_f(__high2float(gh)));
-              const __half2 r = __floats2half2_rn(__low2float(ah) * __low2float(ge), __high2float(ah) * __high2float(ge));
-              o[j] = *reinterpret_cast<const uint32_t*>(&r);
+          for (int jj = 0; jj < 16; ++jj) {
+            float a0 = __uint_as_float(va[2 * jj]), a1 = __uint_as_float(va[2 * jj + 1]);
+            float g0 = __uint_as_float(vg[2 * jj]), g1 = __uint_as_float(vg[2 * jj + 1]);
+            if (p.bias) {
+              const __half2 ba = *reinterpret_cast<const __half2*>(p.bias + na + 2 * jj);
+              const __half2 bg = *reinterpret_cast<const __half2*>(p.bias + ng + 2 * jj);
+              a0 += __low2float(ba);
+              a1 += __high2float(ba);
+              g0 += __low2float(bg);
+              g1 += __high2float(bg);
             }
-            uint4* dst = reinterpret_cast<uint4*>(out_row + c0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            const __half2 ah = __floats2half2_rn(a0, a1);
+            const __half2 gh = __floats2half2_rn(g0, g1);
+            const __half2 ge = __floats2half2_rn(gelu_erf_f(__low2float(gh)), gelu_erf_f(__high2float(gh)));
+            const __half2 r = __floats2half2_rn(__low2float(ah) * __low2float(ge), __high2float(ah) * __high2float(ge));
+            o[jj] = *reinterpret_cast<const uint32_t*>(&r);
           }
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(srow + ((c ^ sw) << 4)) = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
         }
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[as]);
+      mbar_arrive(&tmem_empty_bar[as]);  // accumulator drained: the MMA warp may start the tile after next
+      fence_proxy_async_smem();          // staging tile written by the generic proxy -> visible to TMA
+      named_bar_sync(1, 128);
+      if (leader) {
+#pragma unroll 1
+        for (int j = 0; j < C::EPI_SUB; ++j)
+          tma_store_2d(&map_out, epi_smem + j * C::EPI_SUB_BYTES, n_blk * C::OUT_N + j * 32, m_blk * BM);
+        tma_store_commit();
+        tma_store_wait_read0();  // staging tile has been read out: reusable
+        const int next = tile + gridDim.x;
+        if (full_res && next < num_tiles) issue_residual(next);
+      }
+      named_bar_sync(1, 128);
     }
+    if (leader) tma_store_wait0();
   }
 
   tc_fence_before();
@@ -266,14 +317,15 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
 template <int BN, bool GEGLU>
 void configure_one() {
   CFGPP_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Cfg<BN>::SMEM_BYTES));
+                                        Cfg<BN, GEGLU>::SMEM_BYTES));
 }
 
 template <int BN, bool GEGLU>
 void launch(const GemmOp& op, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, GEGLU>;
   gemm_configure();
-  gemm_kernel<BN, GEGLU><<<op.grid, kThreads, C::SMEM_BYTES, stream>>>(op.p, op.map_a, op.map_a2, op.map_b);
+  gemm_kernel<BN, GEGLU><<<op.grid, kThreads, C::SMEM_BYTES, stream>>>(op.p, op.map_a, op.map_a2, op.map_b, op.map_out,
+                                                                       op.map_res);
   CFGPP_CHECK_CUDA(cudaGetLastError());
 }
 
@@ -309,6 +361,14 @@ void finish_op(GemmOp& op, const __half* w, int force_bn) {
   p.num_m_blocks = (p.M + BM - 1) / BM;
   p.num_n_blocks = (p.N + op.bn - 1) / op.bn;
   op.map_b = make_tmap_2d(w, p.N, p.K, p.K, op.bn);
+  const int n_out = p.geglu ? p.N / 2 : p.N;
+  op.map_out = make_tmap_2d_sw64(p.out, p.M, n_out, p.ldc, BM);
+  if (p.addend != nullptr && p.add_rows_per_group <= 1) {
+    CFGPP_REQUIRE(p.ld_add % 8 == 0, "residual leading dimension must be a multiple of 8");
+    op.map_res = make_tmap_2d_sw64(p.addend, p.M, p.N, p.ld_add, BM);
+  } else {
+    op.map_res = op.map_out;
+  }
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   op.grid = tiles < num_sms() ? tiles : num_sms();
 }

@@ -37,7 +37,7 @@ struct GemmParams {
 };
 
 struct GemmOp {
-  CUtensorMap map_a, map_a2, map_b;
+  CUtensorMap map_a, map_a2, map_b, map_out, map_res;
   GemmParams p;
   int bn;
   int grid;

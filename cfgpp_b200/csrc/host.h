@@ -36,9 +36,11 @@ int num_sms();
 // Generic fp16 tiled tensor map, 128B swizzle. dims/strides innermost first; strides[i] is the byte
 // stride of dim i+1 (dim 0 is contiguous). OOB elements are zero-filled by the hardware.
 CUtensorMap make_tmap_f16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                          const uint32_t* box);
+                          const uint32_t* box, int swizzle_bytes = 128);
 
 // 2D row-major [rows][cols] fp16 with leading dimension ld (elements); box = (64 cols, box_rows).
 CUtensorMap make_tmap_2d(const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+// epilogue tiles: box = (32 cols = 64 B, box_rows), 64B swizzle (output stores / residual loads)
+CUtensorMap make_tmap_2d_sw64(const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 
 }  // namespace cfgpp

@@ -42,10 +42,29 @@ __global__ void gn_stats_kernel(GnSrc src, int HW, int C, int px_per_block, floa
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   const int p0 = chunk * px_per_block;
-  for (int pp = prow; pp < px_per_block; pp += pstep) {
-    const int pix = p0 + pp;
-    if (pix >= HW) break;
-    const uint4 u = load_vec(src, static_cast<size_t>(b) * HW + pix, vec * 8);
+  const int pend = min(px_per_block, HW - p0);
+  const size_t base = static_cast<size_t>(b) * HW + p0;
+  constexpr int U = 4;  // independent 16 B loads in flight per thread
+  int pp = prow;
+  for (; pp + (U - 1) * pstep < pend; pp += U * pstep) {
+    uint4 u[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) u[j] = load_vec(src, base + pp + j * pstep, vec * 8);
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const __half2* h = reinterpret_cast<const __half2*>(&u[j]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        s[2 * i] += f.x;
+        q[2 * i] += f.x * f.x;
+        s[2 * i + 1] += f.y;
+        q[2 * i + 1] += f.y * f.y;
+      }
+    }
+  }
+  for (; pp < pend; pp += pstep) {
+    const uint4 u = load_vec(src, base + pp, vec * 8);
     const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -56,12 +75,10 @@ __global__ void gn_stats_kernel(GnSrc src, int HW, int C, int px_per_block, floa
       q[2 * i + 1] += f.y * f.y;
     }
   }
-  if (prow < pstep) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(&sm[vec * 8 + i], s[i]);
-      atomicAdd(&sm[C + vec * 8 + i], q[i]);
-    }
+  for (int i = 0; i < 8; ++i) {
+    atomicAdd(&sm[vec * 8 + i], s[i]);
+    atomicAdd(&sm[C + vec * 8 + i], q[i]);
   }
   __syncthreads();
   const int cpg = C / GROUPS;
@@ -77,7 +94,8 @@ __global__ void gn_stats_kernel(GnSrc src, int HW, int C, int px_per_block, floa
   }
 }
 
-// grid (ceil(HW / px_per_block), B)
+// grid (nchunk, B); block = vpp * k threads: a thread owns one 8-channel vector, so the per-channel affine
+// ((x - mean) * rstd) * gamma + beta (the reference's evaluation order) uses 32 registers set up once per thread.
 __global__ void gn_apply_kernel(GnSrc src, int HW, int C, int px_per_block, const float* __restrict__ partial,
                                 int nchunk, const __half* __restrict__ gamma, const __half* __restrict__ beta,
                                 float eps, int silu, __half* __restrict__ out) {
@@ -99,26 +117,37 @@ __global__ void gn_apply_kernel(GnSrc src, int HW, int C, int px_per_block, cons
   __syncthreads();
   const int vpp = C >> 3;
   const int cpg = C / GROUPS;
+  const int vec = threadIdx.x % vpp;
+  const int prow = threadIdx.x / vpp;
+  const int pstep = blockDim.x / vpp;
+  const int c0 = vec * 8;
+  float scale[8], shift[8];  // rstd / mean of the group each of this thread's 8 channels belongs to
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int g = (c0 + k) / cpg;
+    scale[k] = s_rstd[g];
+    shift[k] = s_mean[g];
+  }
+  const uint4 ug = *reinterpret_cast<const uint4*>(gamma + c0);
+  const uint4 ub = *reinterpret_cast<const uint4*>(beta + c0);
+  const __half* hg = reinterpret_cast<const __half*>(&ug);
+  const __half* hb = reinterpret_cast<const __half*>(&ub);
+  float gm[8], bt[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    gm[k] = __half2float(hg[k]);
+    bt[k] = __half2float(hb[k]);
+  }
   const int p0 = blockIdx.x * px_per_block;
-  const int total = px_per_block * vpp;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int pp = i / vpp;
-    const int vec = i - pp * vpp;
-    const int pix = p0 + pp;
-    if (pix >= HW) break;
-    const size_t gp = static_cast<size_t>(b) * HW + pix;
-    const int c0 = vec * 8;
-    const uint4 u = load_vec(src, gp, c0);
-    const uint4 ug = *reinterpret_cast<const uint4*>(gamma + c0);
-    const uint4 ub = *reinterpret_cast<const uint4*>(beta + c0);
+  const int pend = min(px_per_block, HW - p0);
+  const size_t base = static_cast<size_t>(b) * HW + p0;
+  constexpr int U = 4;
+  auto emit = [&](const uint4& u, size_t gp) {
     const __half* hx = reinterpret_cast<const __half*>(&u);
-    const __half* hg = reinterpret_cast<const __half*>(&ug);
-    const __half* hb = reinterpret_cast<const __half*>(&ub);
     float y[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int g = (c0 + k) / cpg;
-      float v = (__half2float(hx[k]) - s_mean[g]) * s_rstd[g] * __half2float(hg[k]) + __half2float(hb[k]);
+      float v = (__half2float(hx[k]) - shift[k]) * scale[k] * gm[k] + bt[k];
       if (silu) v = silu_f(v);
       y[k] = v;
     }
@@ -128,7 +157,16 @@ __global__ void gn_apply_kernel(GnSrc src, int HW, int C, int px_per_block, cons
     o.z = pack_half2(y[4], y[5]);
     o.w = pack_half2(y[6], y[7]);
     *reinterpret_cast<uint4*>(out + gp * C + c0) = o;
+  };
+  int pp = prow;
+  for (; pp + (U - 1) * pstep < pend; pp += U * pstep) {
+    uint4 u[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) u[j] = load_vec(src, base + pp + j * pstep, c0);
+#pragma unroll
+    for (int j = 0; j < U; ++j) emit(u[j], base + pp + j * pstep);
   }
+  for (; pp < pend; pp += pstep) emit(load_vec(src, base + pp, c0), base + pp);
 }
 
 // one warp per row; C % 8 == 0, C <= 2048
@@ -216,8 +254,8 @@ void run_groupnorm(const __half* x1, int C1, const __half* x2, int C2, int B, in
   CFGPP_REQUIRE(threads <= 1024, "GroupNorm channel count too large");
   gn_stats_kernel<<<dim3(nchunk, B), threads, 2 * C * sizeof(float), stream>>>(src, HW, C, ppb, partial);
   CFGPP_CHECK_CUDA(cudaGetLastError());
-  gn_apply_kernel<<<dim3(nchunk, B), 256, 0, stream>>>(src, HW, C, ppb, partial, nchunk, gamma, beta, eps,
-                                                       silu ? 1 : 0, out);
+  gn_apply_kernel<<<dim3(nchunk, B), threads, 0, stream>>>(src, HW, C, ppb, partial, nchunk, gamma, beta, eps,
+                                                           silu ? 1 : 0, out);
   CFGPP_CHECK_CUDA(cudaGetLastError());
 }
 
