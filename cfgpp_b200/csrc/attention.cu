@@ -91,6 +91,8 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp_idx == 0) {
     if (lane == 0) {
@@ -302,8 +304,7 @@ void attn_configure() {
 void run_attn_op(const AttnOp& op, cudaStream_t stream) {
   attn_configure();
   dim3 grid((op.p.Nq + 2 * BQ - 1) / (2 * BQ), op.p.H, op.p.B);
-  attn_kernel<<<grid, kThreads, SMEM_BYTES, stream>>>(op.p, op.map_q, op.map_k, op.map_v);
-  CFGPP_CHECK_CUDA(cudaGetLastError());
+  launch_pdl(attn_kernel, grid, dim3(kThreads), SMEM_BYTES, stream, op.p, op.map_q, op.map_k, op.map_v);
 }
 
 }  // namespace cfgpp

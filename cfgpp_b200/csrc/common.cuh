@@ -16,6 +16,15 @@ CFGPP_DEVICE uint32_t smem_u32(const void* p) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): every kernel of the step is launched with the programmatic-stream-
+// serialization attribute. pdl_launch_dependents() lets the next kernel's CTAs start (and run their prologue:
+// barrier init, TMEM alloc, descriptor prefetch) as soon as SM resources free up; pdl_wait() blocks until the
+// preceding kernel has fully completed and its writes are visible — it must precede the first global access.
+// ----------------------------------------------------------------------------------------------
+CFGPP_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+CFGPP_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 CFGPP_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {

@@ -14,6 +14,8 @@ namespace {
 // ------------------------------------------------------------------------------------------------------------
 __global__ void sincos_kernel(const float* __restrict__ vals, int val_stride, int n, int dim,
                               __half* __restrict__ out, int ld, int col_off) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int half_dim = dim >> 1;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * half_dim) return;
@@ -34,6 +36,8 @@ __global__ void small_linear_kernel(const __half* __restrict__ in, int ld_in, co
                                     const __half* __restrict__ bias, const __half* __restrict__ addend, int ld_add,
                                     __half* __restrict__ out, int ld_out, __half* __restrict__ out2, int R, int N,
                                     int K, int out_silu) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -84,6 +88,8 @@ __global__ void small_linear_kernel(const __half* __restrict__ in, int ld_in, co
 
 __global__ void copy_rows_kernel(const __half* __restrict__ src, int src_rows, int cols, __half* __restrict__ dst,
                                  int ld_dst, int col_off, int R) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= R * cols) return;
   const int r = idx / cols, c = idx - r * cols;
@@ -94,6 +100,8 @@ __global__ void copy_rows_kernel(const __half* __restrict__ src, int src_rows, i
 // conv_in: 4 -> Cout, 3x3 pad 1, NCHW latent -> NHWC fp16. thread = (pixel, 8 output channels)
 // ------------------------------------------------------------------------------------------------------------
 __global__ void select_step_kernel(const StepState* __restrict__ table, int* counter, StepState* cur) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = *counter;
   *cur = table[i];
   *counter = i + 1;
@@ -102,6 +110,8 @@ __global__ void select_step_kernel(const StepState* __restrict__ table, int* cou
 __global__ void conv_in_kernel(const void* __restrict__ z, int z_is_half, const float* __restrict__ in_scale_ptr,
                                const __half* __restrict__ w, const __half* __restrict__ bias, __half* __restrict__ out,
                                int B, int H, int W, int Cout, int reps, int px_per_block) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sw[];  // [36][Cout] fp32 (tap-major: ci*9 + kh*3 + kw), then bias [Cout]
   const int use_scale = in_scale_ptr != nullptr;
   const float in_scale = use_scale ? *in_scale_ptr : 1.0f;
@@ -236,6 +246,8 @@ __global__ void conv_out_step_kernel(const __half* __restrict__ x, const __half*
                                      const __half* __restrict__ bias, int B, int H, int W, int Cin, int mode,
                                      int half_state, const StepCoef* __restrict__ coef, void* z, void* aux,
                                      void* z0t_out, __half* __restrict__ eps_uc, __half* __restrict__ eps_c) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __half swh[];  // [4][9][Cin]
   for (int i = threadIdx.x * 8; i < 4 * 9 * Cin; i += blockDim.x * 8)
     *reinterpret_cast<uint4*>(swh + i) = *reinterpret_cast<const uint4*>(w + i);
@@ -305,6 +317,8 @@ __global__ void conv_out_step_kernel(const __half* __restrict__ x, const __half*
 
 __global__ void step_only_kernel(const __half* __restrict__ eps_uc, const __half* __restrict__ eps_c, int n, int mode,
                                  int half_state, const StepCoef* __restrict__ coef, void* z, void* aux, void* z0t_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   apply_step_elem(mode, half_state, *coef, __half2float(eps_uc[i]), __half2float(eps_c[i]), z, aux, z0t_out, i);
@@ -314,6 +328,8 @@ __global__ void step_only_kernel(const __half* __restrict__ eps_uc, const __half
 // resampling helpers (NHWC fp16, 16-byte vectors)
 // ------------------------------------------------------------------------------------------------------------
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int B, int H, int W, int Cv) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t total = static_cast<size_t>(B) * 4 * H * W * Cv;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -328,6 +344,8 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
 }
 
 __global__ void im2col_s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int B, int H, int W, int Cv) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Ho = H >> 1, Wo = W >> 1;
   const size_t total = static_cast<size_t>(B) * Ho * Wo * 9 * Cv;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -352,8 +370,7 @@ __global__ void im2col_s2_kernel(const uint4* __restrict__ x, uint4* __restrict_
 void run_sincos_embed(const float* vals, int val_stride, int n, int dim, __half* out, int ld, int col_off,
                       cudaStream_t stream) {
   const int total = n * (dim / 2);
-  sincos_kernel<<<(total + 255) / 256, 256, 0, stream>>>(vals, val_stride, n, dim, out, ld, col_off);
-  CFGPP_CHECK_CUDA(cudaGetLastError());
+  launch_pdl(sincos_kernel, dim3((total + 255) / 256), dim3(256), 0, stream, vals, val_stride, n, dim, out, ld, col_off);
 }
 
 void run_small_linear(const __half* in, int ld_in, const __half* w, const __half* bias, const __half* addend,
@@ -362,21 +379,18 @@ void run_small_linear(const __half* in, int ld_in, const __half* w, const __half
   CFGPP_REQUIRE(R >= 1 && R <= MAX_R, "small_linear supports 1..16 rows");
   CFGPP_REQUIRE(K % 8 == 0 && ld_in % 8 == 0, "small_linear needs K % 8 == 0");
   const int warps = 8;
-  small_linear_kernel<<<(N + warps - 1) / warps, warps * 32, 0, stream>>>(in, ld_in, w, bias, addend, ld_add, out,
+  launch_pdl(small_linear_kernel, dim3((N + warps - 1) / warps), dim3(warps * 32), 0, stream, in, ld_in, w, bias, addend, ld_add, out,
                                                                           ld_out, out2, R, N, K, out_silu ? 1 : 0);
-  CFGPP_CHECK_CUDA(cudaGetLastError());
 }
 
 void run_copy_rows(const __half* src, int src_rows, int cols, __half* dst, int ld_dst, int col_off, int R,
                    cudaStream_t stream) {
   const int total = R * cols;
-  copy_rows_kernel<<<(total + 255) / 256, 256, 0, stream>>>(src, src_rows, cols, dst, ld_dst, col_off, R);
-  CFGPP_CHECK_CUDA(cudaGetLastError());
+  launch_pdl(copy_rows_kernel, dim3((total + 255) / 256), dim3(256), 0, stream, src, src_rows, cols, dst, ld_dst, col_off, R);
 }
 
 void run_select_step(const StepState* table, int* counter, StepState* cur, cudaStream_t stream) {
-  select_step_kernel<<<1, 1, 0, stream>>>(table, counter, cur);
-  CFGPP_CHECK_CUDA(cudaGetLastError());
+  launch_pdl(select_step_kernel, dim3(1), dim3(1), 0, stream, table, counter, cur);
 }
 
 void run_conv_in(const void* z, int z_is_half, const float* in_scale, const __half* w, const __half* bias,
@@ -390,9 +404,8 @@ void run_conv_in(const void* z, int z_is_half, const float* in_scale, const __ha
     configured = true;
   }
   const int total = B * H * W;
-  conv_in_kernel<<<(total + ppb - 1) / ppb, 320, smem, stream>>>(z, z_is_half, in_scale, w, bias, out, B, H, W, Cout,
+  launch_pdl(conv_in_kernel, dim3((total + ppb - 1) / ppb), dim3(320), smem, stream, z, z_is_half, in_scale, w, bias, out, B, H, W, Cout,
                                                                  reps, ppb);
-  CFGPP_CHECK_CUDA(cudaGetLastError());
 }
 
 // The state dtype travels in bit 8 of `mode` (mode | 0x100 = fp16 sampler state).
@@ -406,35 +419,31 @@ void run_conv_out_step(const __half* x, const __half* w, const __half* bias, int
   CFGPP_REQUIRE(smem <= 48 * 1024, "conv_out weights must fit 48 KB of shared memory");
   const int warps = 8;
   const int total = B * H * W;
-  conv_out_step_kernel<<<(total + warps - 1) / warps, warps * 32, smem, stream>>>(
+  launch_pdl(conv_out_step_kernel, dim3((total + warps - 1) / warps), dim3(warps * 32), smem, stream, 
       x, w, bias, B, H, W, Cin, m, half_state, coef_dev, z, aux, z0t_out, eps_uc, eps_c);
-  CFGPP_CHECK_CUDA(cudaGetLastError());
 }
 
 void run_step_only(const __half* eps_uc, const __half* eps_c, int n, int mode, const StepCoef* coef_dev, void* z,
                    void* aux, void* z0t_out, cudaStream_t stream) {
   const int half_state = (mode & 0x100) ? 1 : 0;
-  step_only_kernel<<<(n + 255) / 256, 256, 0, stream>>>(eps_uc, eps_c, n, mode & 0xff, half_state, coef_dev, z, aux,
+  launch_pdl(step_only_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, eps_uc, eps_c, n, mode & 0xff, half_state, coef_dev, z, aux,
                                                         z0t_out);
-  CFGPP_CHECK_CUDA(cudaGetLastError());
 }
 
 void run_upsample2x(const __half* x, __half* out, int B, int H, int W, int C, cudaStream_t stream) {
   CFGPP_REQUIRE(C % 8 == 0, "upsample C % 8");
   const size_t total = static_cast<size_t>(B) * 4 * H * W * (C / 8);
   const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 16));
-  upsample2x_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), B, H,
+  launch_pdl(upsample2x_kernel, dim3(blocks), dim3(256), 0, stream, reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), B, H,
                                                 W, C / 8);
-  CFGPP_CHECK_CUDA(cudaGetLastError());
 }
 
 void run_im2col_s2(const __half* x, __half* out, int B, int H, int W, int C, cudaStream_t stream) {
   CFGPP_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "im2col_s2 shape");
   const size_t total = static_cast<size_t>(B) * (H / 2) * (W / 2) * 9 * (C / 8);
   const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 16));
-  im2col_s2_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), B, H,
+  launch_pdl(im2col_s2_kernel, dim3(blocks), dim3(256), 0, stream, reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), B, H,
                                                W, C / 8);
-  CFGPP_CHECK_CUDA(cudaGetLastError());
 }
 
 }  // namespace cfgpp

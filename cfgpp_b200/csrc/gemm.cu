@@ -86,6 +86,8 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_launch_dependents();  // the next kernel may start its prologue on SMs this grid leaves
+  pdl_wait();               // everything above overlapped the previous kernel's tail; its outputs are needed below
 
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
   const int nkb = p.num_k_blocks;
@@ -324,9 +326,8 @@ template <int BN, bool GEGLU>
 void launch(const GemmOp& op, cudaStream_t stream) {
   using C = Cfg<BN, GEGLU>;
   gemm_configure();
-  gemm_kernel<BN, GEGLU><<<op.grid, kThreads, C::SMEM_BYTES, stream>>>(op.p, op.map_a, op.map_a2, op.map_b, op.map_out,
-                                                                       op.map_res);
-  CFGPP_CHECK_CUDA(cudaGetLastError());
+  launch_pdl(gemm_kernel<BN, GEGLU>, dim3(op.grid), dim3(kThreads), C::SMEM_BYTES, stream, op.p, op.map_a, op.map_a2,
+             op.map_b, op.map_out, op.map_res);
 }
 
 // tile-width heuristic: fewest (waves x per-tile cost) over the allowed widths

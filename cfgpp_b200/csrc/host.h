@@ -8,6 +8,7 @@
 
 #include <stdexcept>
 #include <string>
+#include <utility>
 
 namespace cfgpp {
 
@@ -32,6 +33,23 @@ struct Error : public std::runtime_error {
   } while (0)
 
 int num_sms();
+
+// Launch with programmatic dependent launch enabled (see common.cuh). Capturable into CUDA graphs.
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                       Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CFGPP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...));
+}
 
 // Generic fp16 tiled tensor map, 128B swizzle. dims/strides innermost first; strides[i] is the byte
 // stride of dim i+1 (dim 0 is contiguous). OOB elements are zero-filled by the hardware.

@@ -29,6 +29,8 @@ CFGPP_DEVICE uint4 load_vec(const GnSrc& s, size_t pix, int c) {  // c multiple 
 
 // grid (nchunk, B); block = vpp * k threads (vpp = C / 8 vectors per pixel) so a thread keeps one channel vector.
 __global__ void gn_stats_kernel(GnSrc src, int HW, int C, int px_per_block, float* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];  // [C] sums, [C] sumsq
   const int vpp = C >> 3;
   const int b = blockIdx.y;
@@ -99,6 +101,8 @@ __global__ void gn_stats_kernel(GnSrc src, int HW, int C, int px_per_block, floa
 __global__ void gn_apply_kernel(GnSrc src, int HW, int C, int px_per_block, const float* __restrict__ partial,
                                 int nchunk, const __half* __restrict__ gamma, const __half* __restrict__ beta,
                                 float eps, int silu, __half* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_mean[GROUPS], s_rstd[GROUPS];
   const int b = blockIdx.y;
   if (threadIdx.x < GROUPS) {
@@ -172,6 +176,8 @@ __global__ void gn_apply_kernel(GnSrc src, int HW, int C, int px_per_block, cons
 // one warp per row; C % 8 == 0, C <= 2048
 __global__ void layernorm_kernel(const __half* __restrict__ x, int M, int C, const __half* __restrict__ gamma,
                                  const __half* __restrict__ beta, float eps, __half* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -252,19 +258,16 @@ void run_groupnorm(const __half* x1, int C1, const __half* x2, int C2, int B, in
   if (k < 1) k = 1;
   const int threads = vpp * k;
   CFGPP_REQUIRE(threads <= 1024, "GroupNorm channel count too large");
-  gn_stats_kernel<<<dim3(nchunk, B), threads, 2 * C * sizeof(float), stream>>>(src, HW, C, ppb, partial);
-  CFGPP_CHECK_CUDA(cudaGetLastError());
-  gn_apply_kernel<<<dim3(nchunk, B), threads, 0, stream>>>(src, HW, C, ppb, partial, nchunk, gamma, beta, eps,
+  launch_pdl(gn_stats_kernel, dim3(nchunk, B), dim3(threads), 2 * C * sizeof(float), stream, src, HW, C, ppb, partial);
+  launch_pdl(gn_apply_kernel, dim3(nchunk, B), dim3(threads), 0, stream, src, HW, C, ppb, partial, nchunk, gamma, beta, eps,
                                                            silu ? 1 : 0, out);
-  CFGPP_CHECK_CUDA(cudaGetLastError());
 }
 
 void run_layernorm(const __half* x, int M, int C, const __half* gamma, const __half* beta, float eps, __half* out,
                    cudaStream_t stream) {
   CFGPP_REQUIRE(C % 8 == 0 && C <= 2048, "LayerNorm needs C % 8 == 0 and C <= 2048");
   const int warps = 8;
-  layernorm_kernel<<<(M + warps - 1) / warps, warps * 32, 0, stream>>>(x, M, C, gamma, beta, eps, out);
-  CFGPP_CHECK_CUDA(cudaGetLastError());
+  launch_pdl(layernorm_kernel, dim3((M + warps - 1) / warps), dim3(warps * 32), 0, stream, x, M, C, gamma, beta, eps, out);
 }
 
 }  // namespace cfgpp

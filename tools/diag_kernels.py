@@ -376,6 +376,52 @@ def diag_unet(which=("tiny_sdxl", "tiny_sd15")):
         guarded(label, run)
 
 
+def prof_unet():
+    """Per-plan-entry CUDA-event profile of one eager SDXL forward (batch 2), aggregated by op type."""
+    import collections
+    import re
+    from cfgpp_b200 import config as C, weights as Wt
+    from cfgpp_b200.engine import NativeUNet
+    cfg = C.sdxl_config()
+    B, hw = 2, 128
+    sd = Wt.synthetic_state_dict(cfg, seed=1234, device=dev)
+    z, uc, c, add = _unet_inputs(cfg, B, hw)
+    net = NativeUNet(cfg, sd, dev)
+    del sd
+    net.prepare(B, hw, hw)
+    net.set_prompt(torch.cat([uc, c]), add["text_embeds"], add["time_ids"].float())
+    net.profile_forward(z, 500.0)
+    prof = net.profile_forward(z, 500.0)
+    agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
+    for name, kind, fl, ms in prof:
+        lvl = "L?"
+        m = re.match(r"(down_blocks|up_blocks)\.(\d)", name)
+        if m:
+            i = int(m.group(2))
+            lvl = f"L{i}" if m.group(1) == "down_blocks" else f"L{2 - i}"
+        elif name.startswith("mid_block"):
+            lvl = "L2"
+        short = re.sub(r"^.*?(resnets|attentions|downsamplers|upsamplers)\.\d+\.", "", name)
+        short = re.sub(r"transformer_blocks\.\d+\.", "", short)
+        key = (lvl, short, kind)
+        agg[key][0] += 1
+        agg[key][1] += ms
+        agg[key][2] += fl
+    tot = sum(v[1] for v in agg.values())
+    print(f"total (eager, event-timed per entry) {tot:.2f} ms", flush=True)
+    for (lvl, short, kind), (n, ms, fl) in sorted(agg.items(), key=lambda x: -x[1][1])[:40]:
+        tf = fl / ms / 1e9 if ms > 0 and fl > 0 else 0
+        print(f"  {ms:7.3f} ms {100*ms/tot:5.1f}%  n={n:3d} avg={1e3*ms/n:7.1f} us  {tf:6.0f} TF/s  {lvl} {short} kind={kind}", flush=True)
+    bk = collections.defaultdict(lambda: [0.0, 0.0])
+    for name, kind, fl, ms in prof:
+        bk[kind][0] += ms
+        bk[kind][1] += fl
+    for k, nm in [(0, "linear"), (1, "conv3x3"), (2, "attention"), (3, "other")]:
+        ms, fl = bk[k]
+        print(f"  kind {nm}: {ms:.2f} ms  {fl/ms/1e9 if ms else 0:.0f} TF/s", flush=True)
+    net.close()
+
+
 def bench_unet():
     """First end-to-end timing of the SDXL step (B=2 -> UNet batch 4) vs the eager fp16-autocast oracle."""
     from cfgpp_b200 import config as C, weights as Wt, schedule as S
@@ -447,5 +493,7 @@ if __name__ == "__main__":
         diag_unet(("sdxl",))
     if "bench_unet" in which:
         bench_unet()
+    if "prof_unet" in which:
+        prof_unet()
     nbad = sum(1 for _, ok in RESULTS if not ok)
     print(f"=== {len(RESULTS) - nbad}/{len(RESULTS)} cases OK in {time.time() - t0:.1f}s ===", flush=True)
