@@ -3,6 +3,7 @@
 
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <mutex>
 
 namespace cfgpp {
@@ -15,6 +16,15 @@ int num_sms() {
     CFGPP_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
   }
   return n;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CFGPP_NO_PDL");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {

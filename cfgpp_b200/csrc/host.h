@@ -33,6 +33,7 @@ struct Error : public std::runtime_error {
   } while (0)
 
 int num_sms();
+bool pdl_enabled();  // false when CFGPP_NO_PDL=1 is set in the environment (A/B switch)
 
 // Launch with programmatic dependent launch enabled (see common.cuh). Capturable into CUDA graphs.
 template <typename... KArgs, typename... Args>
@@ -47,7 +48,7 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
   CFGPP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...));
 }
 

@@ -31,12 +31,10 @@ CFGPP_DEVICE uint4 load_vec(const GnSrc& s, size_t pix, int c) {  // c multiple 
 __global__ void gn_stats_kernel(GnSrc src, int HW, int C, int px_per_block, float* __restrict__ partial) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ float sm[];  // [C] sums, [C] sumsq
+  extern __shared__ float sm[];  // [pstep][C] sums, then [pstep][C] sums of squares (one slot per thread: no atomics)
   const int vpp = C >> 3;
   const int b = blockIdx.y;
   const int chunk = blockIdx.x;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
   const int vec = threadIdx.x % vpp;
   const int prow = threadIdx.x / vpp;
   const int pstep = blockDim.x / vpp;
@@ -77,19 +75,21 @@ __global__ void gn_stats_kernel(GnSrc src, int HW, int C, int px_per_block, floa
       q[2 * i + 1] += f.y * f.y;
     }
   }
+  float* sq = sm + pstep * C;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    atomicAdd(&sm[vec * 8 + i], s[i]);
-    atomicAdd(&sm[C + vec * 8 + i], q[i]);
+    sm[prow * C + vec * 8 + i] = s[i];
+    sq[prow * C + vec * 8 + i] = q[i];
   }
   __syncthreads();
   const int cpg = C / GROUPS;
-  if (threadIdx.x < GROUPS) {
+  if (threadIdx.x < GROUPS) {  // fixed summation order -> bit-reproducible statistics
     float a = 0.f, bsum = 0.f;
-    for (int i = 0; i < cpg; ++i) {
-      a += sm[threadIdx.x * cpg + i];
-      bsum += sm[C + threadIdx.x * cpg + i];
-    }
+    for (int r = 0; r < pstep; ++r)
+      for (int i = 0; i < cpg; ++i) {
+        a += sm[r * C + threadIdx.x * cpg + i];
+        bsum += sq[r * C + threadIdx.x * cpg + i];
+      }
     float* dst = partial + ((static_cast<size_t>(b) * gridDim.x + chunk) * GROUPS + threadIdx.x) * 2;
     dst[0] = a;
     dst[1] = bsum;
@@ -258,7 +258,8 @@ void run_groupnorm(const __half* x1, int C1, const __half* x2, int C2, int B, in
   if (k < 1) k = 1;
   const int threads = vpp * k;
   CFGPP_REQUIRE(threads <= 1024, "GroupNorm channel count too large");
-  launch_pdl(gn_stats_kernel, dim3(nchunk, B), dim3(threads), 2 * C * sizeof(float), stream, src, HW, C, ppb, partial);
+  launch_pdl(gn_stats_kernel, dim3(nchunk, B), dim3(threads), 2 * static_cast<size_t>(k) * C * sizeof(float), stream, src, HW, C,
+             ppb, partial);
   launch_pdl(gn_apply_kernel, dim3(nchunk, B), dim3(threads), 0, stream, src, HW, C, ppb, partial, nchunk, gamma, beta, eps,
                                                            silu ? 1 : 0, out);
 }
