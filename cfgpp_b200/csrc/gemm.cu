@@ -6,6 +6,8 @@
 //   warps 4..7    : epilogue      (tcgen05.ld 32x32b -> bias/addend/GEGLU -> fp16 global stores)
 // Pipelines: smem ring full/empty (TMA <-> MMA) and a 2-deep TMEM accumulator ring full/empty (MMA <-> epilogue),
 // so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "gemm.cuh"
 
@@ -36,7 +38,11 @@ struct Cfg {
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of an SM");
 };
 
-template <int BN, bool GEGLU>
+// CL = thread-block-cluster size along M (1 or 2). With CL = 2 the two CTAs work on vertically adjacent tiles of
+// the same N block and each loads only half of the shared B (weight) tile, multicasting it into both CTAs' shared
+// memory: L2 -> SM traffic per output element drops by the B share, which is what bounds the 128 x 160 tiles
+// (measured ~11 TB/s L2 -> SM  =>  ~790 TFLOP/s at 71 FLOP/B).
+template <int BN, bool GEGLU, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
             const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
@@ -58,6 +64,10 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cta_rank = (CL > 1) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cluster_id = blockIdx.x / CL;
+  const int num_clusters = gridDim.x / CL;
+  constexpr uint16_t kMask = (1u << CL) - 1;
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -69,7 +79,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
   if (warp_idx == 1 && lane == 0) {
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CL);  // released by the MMA warps of every CTA that receives the multicast B half
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
@@ -84,22 +94,28 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();  // peer barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_launch_dependents();  // the next kernel may start its prologue on SMs this grid leaves
   pdl_wait();               // everything above overlapped the previous kernel's tail; its outputs are needed below
 
-  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  // tiles are enumerated as (m-group, n) with CL vertically adjacent M blocks per group; a cluster walks the groups,
+  // CTA `cta_rank` takes M block  group * CL + cta_rank  (possibly a phantom block past M: loads zero-fill, stores clip)
+  const int num_mg = (p.num_m_blocks + CL - 1) / CL;
+  const int num_tiles = num_mg * p.num_n_blocks;
   const int nkb = p.num_k_blocks;
+  auto tile_m_blk = [&](int tile) { return (tile % num_mg) * CL + cta_rank; };
+  auto tile_n_blk = [&](int tile) { return tile / num_mg; };
 
   if (warp_idx == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % p.num_m_blocks;
-        const int n_blk = tile / p.num_m_blocks;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = tile_m_blk(tile);
+        const int n_blk = tile_n_blk(tile);
         const int m0 = m_blk * BM;
         int img = 0, h0 = 0, w0 = 0;
         if (p.conv) {
@@ -126,7 +142,13 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
             else
               tma_load_2d(sa, &map_a2, &full_bar[stage], k0 - p.k_split, m0);
           }
-          tma_load_2d(sb, &map_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if constexpr (CL == 1) {
+            tma_load_2d(sb, &map_b, &full_bar[stage], kb * BK, n_blk * BN);
+          } else {
+            constexpr int HALF = BN / CL;  // rows of the B tile this CTA fetches for the whole cluster
+            tma_load_2d_mcast(sb + cta_rank * HALF * BK * 2, &map_b, &full_bar[stage], kb * BK,
+                              n_blk * BN + cta_rank * HALF, kMask);
+          }
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -141,7 +163,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&tmem_empty_bar[as], aph ^ 1);
@@ -159,7 +181,11 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
             // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
             umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          // frees the smem slot (in every CTA of the cluster: the peer's multicast writes into ours) on retirement
+          if constexpr (CL == 1)
+            umma_commit(&empty_bar[stage]);
+          else
+            umma_commit_mcast(&empty_bar[stage], kMask);
           if (kb == nkb - 1) umma_commit(&tmem_full_bar[as]);
           if (++stage == C::STAGES) {
             stage = 0;
@@ -181,20 +207,20 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
     const int sw = (row >> 1) & 3;  // 64B swizzle: 16-byte chunk index ^= (row / 2) % 4
     uint8_t* my_row = epi_smem + row * 64;
     auto issue_residual = [&](int tile) {
-      const int m_blk = tile % p.num_m_blocks;
-      const int n_blk = tile / p.num_m_blocks;
+      const int m_blk = tile_m_blk(tile);
+      const int n_blk = tile_n_blk(tile);
       mbar_arrive_expect_tx(res_full_bar, C::EPI_BYTES);
 #pragma unroll 1
       for (int j = 0; j < C::EPI_SUB; ++j)
         tma_load_2d(epi_smem + j * C::EPI_SUB_BYTES, &map_res, res_full_bar, n_blk * C::OUT_N + j * 32, m_blk * BM);
     };
-    if (full_res && leader && static_cast<int>(blockIdx.x) < num_tiles) issue_residual(blockIdx.x);
+    if (full_res && leader && cluster_id < num_tiles) issue_residual(cluster_id);
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
-      const int m_blk = tile % p.num_m_blocks;
-      const int n_blk = tile / p.num_m_blocks;
+      const int m_blk = tile_m_blk(tile);
+      const int n_blk = tile_n_blk(tile);
       const int m = m_blk * BM + row;
       mbar_wait(&tmem_full_bar[as], aph);
       tc_fence_after();
@@ -300,7 +326,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
           tma_store_2d(&map_out, epi_smem + j * C::EPI_SUB_BYTES, n_blk * C::OUT_N + j * 32, m_blk * BM);
         tma_store_commit();
         tma_store_wait_read0();  // staging tile has been read out: reusable
-        const int next = tile + gridDim.x;
+        const int next = tile + num_clusters;
         if (full_res && next < num_tiles) issue_residual(next);
       }
       named_bar_sync(1, 128);
@@ -310,6 +336,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();  // no CTA leaves while its peer may still multicast / arrive into it
   if (warp_idx == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -318,7 +345,9 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
 
 template <int BN, bool GEGLU>
 void configure_one() {
-  CFGPP_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CFGPP_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, GEGLU, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg<BN, GEGLU>::SMEM_BYTES));
+  CFGPP_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, GEGLU, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg<BN, GEGLU>::SMEM_BYTES));
 }
 
@@ -326,8 +355,21 @@ template <int BN, bool GEGLU>
 void launch(const GemmOp& op, cudaStream_t stream) {
   using C = Cfg<BN, GEGLU>;
   gemm_configure();
-  launch_pdl(gemm_kernel<BN, GEGLU>, dim3(op.grid), dim3(kThreads), C::SMEM_BYTES, stream, op.p, op.map_a, op.map_a2,
-             op.map_b, op.map_out, op.map_res);
+  if (op.cluster == 2)
+    launch_pdl_cluster(gemm_kernel<BN, GEGLU, 2>, dim3(op.grid), dim3(kThreads), C::SMEM_BYTES, stream, 2, op.p,
+                       op.map_a, op.map_a2, op.map_b, op.map_out, op.map_res);
+  else
+    launch_pdl_cluster(gemm_kernel<BN, GEGLU, 1>, dim3(op.grid), dim3(kThreads), C::SMEM_BYTES, stream, 1, op.p,
+                       op.map_a, op.map_a2, op.map_b, op.map_out, op.map_res);
+}
+
+bool cluster_disabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CFGPP_NO_CLUSTER");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
 }
 
 // tile-width heuristic: fewest (waves x per-tile cost) over the allowed widths
@@ -361,7 +403,8 @@ void finish_op(GemmOp& op, const __half* w, int force_bn) {
   if (p.geglu) CFGPP_REQUIRE(op.bn == 256 && p.N % 256 == 0, "GEGLU needs N % 256 == 0");
   p.num_m_blocks = (p.M + BM - 1) / BM;
   p.num_n_blocks = (p.N + op.bn - 1) / op.bn;
-  op.map_b = make_tmap_2d(w, p.N, p.K, p.K, op.bn);
+  op.cluster = (p.num_m_blocks >= 2 && !cluster_disabled()) ? 2 : 1;
+  op.map_b = make_tmap_2d(w, p.N, p.K, p.K, op.bn / op.cluster);
   const int n_out = p.geglu ? p.N / 2 : p.N;
   op.map_out = make_tmap_2d_sw64(p.out, p.M, n_out, p.ldc, BM);
   if (p.addend != nullptr && p.add_rows_per_group <= 1) {
@@ -370,8 +413,9 @@ void finish_op(GemmOp& op, const __half* w, int force_bn) {
   } else {
     op.map_res = op.map_out;
   }
-  const int tiles = p.num_m_blocks * p.num_n_blocks;
-  op.grid = tiles < num_sms() ? tiles : num_sms();
+  const int groups = ((p.num_m_blocks + op.cluster - 1) / op.cluster) * p.num_n_blocks;
+  const int max_clusters = num_sms() / op.cluster;
+  op.grid = op.cluster * (groups < max_clusters ? groups : max_clusters);
 }
 
 }  // namespace

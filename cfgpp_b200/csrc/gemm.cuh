@@ -41,6 +41,7 @@ struct GemmOp {
   GemmParams p;
   int bn;
   int grid;
+  int cluster;  // thread-block-cluster size along M (1 or 2)
   // FLOP accounting (algorithmic): 2*M*N*K
   double flops() const { return 2.0 * p.M * (double)p.N * p.K; }
 };
