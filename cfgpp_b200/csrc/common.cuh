@@ -119,23 +119,62 @@ CFGPP_DEVICE void cluster_sync_all() {  // all threads of all CTAs in the cluste
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// TMA load multicast to the CTAs in cta_mask: data and the mbarrier complete_tx land at the same CTA-relative
-// offsets in every destination CTA.
-CFGPP_DEVICE void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
-                                    uint16_t cta_mask) {
+// ---- cta_group::2 (CTA pair) variants -------------------------------------------------------------------------
+// In a pair the even CTA (cluster rank 0) is the leader: it alone issues tcgen05.mma.cta_group::2, which reads A / B
+// from BOTH CTAs' shared memory (same offsets) and writes each CTA's half of the 256-row accumulator into that CTA's
+// TMEM. Clearing bit 24 of a shared::cluster address gives the same offset in the leader CTA.
+constexpr uint32_t kLeaderMask = 0xFEFFFFFFu;
+
+CFGPP_DEVICE void tmem_alloc_cg2(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+}
+CFGPP_DEVICE void tmem_relinquish_cg2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+CFGPP_DEVICE void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA load into this CTA's shared memory, completion signalled on the LEADER CTA's mbarrier (same offset)
+CFGPP_DEVICE void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
-      "%4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kLeaderMask), "r"(c0), "r"(c1)
       : "memory");
 }
-// tcgen05.commit arriving on the mbarrier at the same offset in every CTA of cta_mask
-CFGPP_DEVICE void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+CFGPP_DEVICE void tma_load_4d_cg2(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                  int c3) {
   asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-          smem_u32(bar)),
-      "h"(cta_mask)
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kLeaderMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+CFGPP_DEVICE void umma_f16_cg2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit of the pair's MMAs, arriving on the mbarrier at this offset in both CTAs
+CFGPP_DEVICE void umma_commit_cg2(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+// arrive on the leader CTA's copy of a barrier (works from either CTA of the pair)
+CFGPP_DEVICE void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kLeaderMask)
+               : "memory");
 }
 
 // generic-proxy smem writes -> visible to the async proxy (UMMA / TMA reads)

@@ -22,32 +22,36 @@ constexpr int BK = 64;
 constexpr int kThreads = 256;
 constexpr int A_BYTES = BM * BK * 2;
 
-template <int BN, bool GEGLU>
+template <int BN, bool GEGLU, int CL = 1>
 struct Cfg {
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / CL) * BK * 2;  // per CTA: a CTA pair (CL = 2) holds half of the B tile each
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // output columns of a tile and its smem staging area: OUT_N / 32 sub-tiles of [128 rows x 64 B], 64B swizzle
   static constexpr int OUT_N = GEGLU ? BN / 2 : BN;
   static constexpr int EPI_SUB = OUT_N / 32;
   static constexpr int EPI_SUB_BYTES = BM * 64;
   static constexpr int EPI_BYTES = EPI_SUB * EPI_SUB_BYTES;
-  static constexpr int STAGES = GEGLU ? 4 : (BN == 256 ? 3 : (BN == 160 ? 5 : 6));
+  static constexpr int STAGES =
+      CL == 2 ? (GEGLU ? 6 : (BN == 256 ? 5 : 6)) : (GEGLU ? 4 : (BN == 256 ? 3 : (BN == 160 ? 5 : 6)));
   static constexpr int TMEM_COLS = (BN <= 64) ? 128 : (BN <= 128 ? 256 : 512);
   static constexpr int ACC_STRIDE = TMEM_COLS / 2;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of an SM");
 };
 
-// CL = thread-block-cluster size along M (1 or 2). With CL = 2 the two CTAs work on vertically adjacent tiles of
-// the same N block and each loads only half of the shared B (weight) tile, multicasting it into both CTAs' shared
-// memory: L2 -> SM traffic per output element drops by the B share, which is what bounds the 128 x 160 tiles
-// (measured ~11 TB/s L2 -> SM  =>  ~790 TFLOP/s at 71 FLOP/B).
+// CL = 1: one CTA per 128 x BN tile (tcgen05.mma.cta_group::1).
+// CL = 2: a CTA pair (cluster of 2 on one TPC) computes a 256 x BN tile with tcgen05.mma.cta_group::2: each CTA
+//         loads its own 128 rows of A and only HALF of the B (weight) tile; the leader's MMA reads both halves
+//         through the pair's shared memory. Per-SM ingest from L2 (64 B/clk/SM, the measured bound of the 128 x 160
+//         tiles: ~13 TB/s aggregate => ~800 TFLOP/s at 71 FLOP/B) drops from (128 + BN) to (128 + BN/2) rows per
+//         k-block. (A plain TMA-multicast of B inside the cluster was tried first and does not help: every SM still
+//         ingests the full tile.)
 template <int BN, bool GEGLU, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
             const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
             const __grid_constant__ CUtensorMap map_res) {
-  using C = Cfg<BN, GEGLU>;
+  using C = Cfg<BN, GEGLU, CL>;
   extern __shared__ uint8_t smem_raw[];
   // 1024B alignment (required by the 128B swizzle atoms) in the shared address space
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -67,7 +71,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
   const int cta_rank = (CL > 1) ? static_cast<int>(cluster_ctarank()) : 0;
   const int cluster_id = blockIdx.x / CL;
   const int num_clusters = gridDim.x / CL;
-  constexpr uint16_t kMask = (1u << CL) - 1;
+  const bool is_leader_cta = (cta_rank == 0);
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -79,22 +83,28 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
   if (warp_idx == 1 && lane == 0) {
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], CL);  // released by the MMA warps of every CTA that receives the multicast B half
+      mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 128);
+      mbar_init(&tmem_empty_bar[i], CL == 2 ? 2 : 128);  // pair: one elected arrive per CTA on the leader's barrier
     }
     mbar_init(res_full_bar, 1);
     fence_barrier_init();
   }
+  if constexpr (CL > 1) cluster_sync_all();  // both CTAs resident before the pair-wide TMEM allocation
   if (warp_idx == 2) {
-    tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CL == 2) {
+      tmem_alloc_cg2(tmem_ptr_smem, C::TMEM_COLS);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (CL > 1) cluster_sync_all();  // peer barriers are initialised before any remote arrive / multicast
+  if constexpr (CL > 1) cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_launch_dependents();  // the next kernel may start its prologue on SMs this grid leaves
@@ -129,25 +139,37 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-          if (p.conv) {
-            const int tap = kb / p.cpb;
-            const int cb = kb - tap * p.cpb;
-            const int kh = tap / 3, kw = tap - kh * 3;
-            tma_load_4d(sa, &map_a, &full_bar[stage], cb * BK, w0 + kw - 1, h0 + kh - 1, img);
-          } else {
-            const int k0 = kb * BK;
-            if (k0 < p.k_split)
-              tma_load_2d(sa, &map_a, &full_bar[stage], k0, m0);
-            else
-              tma_load_2d(sa, &map_a2, &full_bar[stage], k0 - p.k_split, m0);
-          }
           if constexpr (CL == 1) {
+            mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+            if (p.conv) {
+              const int tap = kb / p.cpb;
+              const int cb = kb - tap * p.cpb;
+              const int kh = tap / 3, kw = tap - kh * 3;
+              tma_load_4d(sa, &map_a, &full_bar[stage], cb * BK, w0 + kw - 1, h0 + kh - 1, img);
+            } else {
+              const int k0 = kb * BK;
+              if (k0 < p.k_split)
+                tma_load_2d(sa, &map_a, &full_bar[stage], k0, m0);
+              else
+                tma_load_2d(sa, &map_a2, &full_bar[stage], k0 - p.k_split, m0);
+            }
             tma_load_2d(sb, &map_b, &full_bar[stage], kb * BK, n_blk * BN);
           } else {
-            constexpr int HALF = BN / CL;  // rows of the B tile this CTA fetches for the whole cluster
-            tma_load_2d_mcast(sb + cta_rank * HALF * BK * 2, &map_b, &full_bar[stage], kb * BK,
-                              n_blk * BN + cta_rank * HALF, kMask);
+            // both CTAs fill their own smem; all bytes are accounted on the leader's barrier (the MMA issuer's)
+            if (is_leader_cta) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+            if (p.conv) {
+              const int tap = kb / p.cpb;
+              const int cb = kb - tap * p.cpb;
+              const int kh = tap / 3, kw = tap - kh * 3;
+              tma_load_4d_cg2(sa, &map_a, &full_bar[stage], cb * BK, w0 + kw - 1, h0 + kh - 1, img);
+            } else {
+              const int k0 = kb * BK;
+              if (k0 < p.k_split)
+                tma_load_2d_cg2(sa, &map_a, &full_bar[stage], k0, m0);
+              else
+                tma_load_2d_cg2(sa, &map_a2, &full_bar[stage], k0 - p.k_split, m0);
+            }
+            tma_load_2d_cg2(sb, &map_b, &full_bar[stage], kb * BK, n_blk * BN + cta_rank * (BN / 2));
           }
           if (++stage == C::STAGES) {
             stage = 0;
@@ -157,9 +179,9 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
       }
     }
   } else if (warp_idx == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = make_idesc_f16(BM, BN, 0, 0);
+    if (lane == 0 && is_leader_cta) {
+      // ===================== MMA issuer (pair: leader CTA only) =====================
+      constexpr uint32_t idesc = make_idesc_f16(BM * CL, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -179,14 +201,19 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (CL == 1)
+              umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_f16_cg2(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          // frees the smem slot (in every CTA of the cluster: the peer's multicast writes into ours) on retirement
-          if constexpr (CL == 1)
+          // on retirement: free the smem slot (pair: in both CTAs) and, after the last k-block, publish the accumulator
+          if constexpr (CL == 1) {
             umma_commit(&empty_bar[stage]);
-          else
-            umma_commit_mcast(&empty_bar[stage], kMask);
-          if (kb == nkb - 1) umma_commit(&tmem_full_bar[as]);
+            if (kb == nkb - 1) umma_commit(&tmem_full_bar[as]);
+          } else {
+            umma_commit_cg2(&empty_bar[stage]);
+            if (kb == nkb - 1) umma_commit_cg2(&tmem_full_bar[as]);
+          }
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -317,10 +344,11 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
         }
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[as]);  // accumulator drained: the MMA warp may start the tile after next
-      fence_proxy_async_smem();          // staging tile written by the generic proxy -> visible to TMA
+      if constexpr (CL == 1) mbar_arrive(&tmem_empty_bar[as]);  // accumulator drained: MMA may reuse this stage
+      fence_proxy_async_smem();  // staging tile written by the generic proxy -> visible to TMA
       named_bar_sync(1, 128);
       if (leader) {
+        if constexpr (CL == 2) mbar_arrive_leader(&tmem_empty_bar[as]);  // this CTA's half of the pair accumulator
 #pragma unroll 1
         for (int j = 0; j < C::EPI_SUB; ++j)
           tma_store_2d(&map_out, epi_smem + j * C::EPI_SUB_BYTES, n_blk * C::OUT_N + j * 32, m_blk * BM);
@@ -339,28 +367,30 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
   if constexpr (CL > 1) cluster_sync_all();  // no CTA leaves while its peer may still multicast / arrive into it
   if (warp_idx == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if constexpr (CL == 2)
+      tmem_dealloc_cg2(tmem_base, C::TMEM_COLS);
+    else
+      tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
 template <int BN, bool GEGLU>
 void configure_one() {
   CFGPP_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, GEGLU, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Cfg<BN, GEGLU>::SMEM_BYTES));
+                                        Cfg<BN, GEGLU, 1>::SMEM_BYTES));
   CFGPP_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, GEGLU, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Cfg<BN, GEGLU>::SMEM_BYTES));
+                                        Cfg<BN, GEGLU, 2>::SMEM_BYTES));
 }
 
 template <int BN, bool GEGLU>
 void launch(const GemmOp& op, cudaStream_t stream) {
-  using C = Cfg<BN, GEGLU>;
   gemm_configure();
   if (op.cluster == 2)
-    launch_pdl_cluster(gemm_kernel<BN, GEGLU, 2>, dim3(op.grid), dim3(kThreads), C::SMEM_BYTES, stream, 2, op.p,
-                       op.map_a, op.map_a2, op.map_b, op.map_out, op.map_res);
+    launch_pdl_cluster(gemm_kernel<BN, GEGLU, 2>, dim3(op.grid), dim3(kThreads), Cfg<BN, GEGLU, 2>::SMEM_BYTES, stream,
+                       2, op.p, op.map_a, op.map_a2, op.map_b, op.map_out, op.map_res);
   else
-    launch_pdl_cluster(gemm_kernel<BN, GEGLU, 1>, dim3(op.grid), dim3(kThreads), C::SMEM_BYTES, stream, 1, op.p,
-                       op.map_a, op.map_a2, op.map_b, op.map_out, op.map_res);
+    launch_pdl_cluster(gemm_kernel<BN, GEGLU, 1>, dim3(op.grid), dim3(kThreads), Cfg<BN, GEGLU, 1>::SMEM_BYTES, stream,
+                       1, op.p, op.map_a, op.map_a2, op.map_b, op.map_out, op.map_res);
 }
 
 bool cluster_disabled() {
