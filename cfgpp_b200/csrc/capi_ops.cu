@@ -22,6 +22,25 @@ CFGPP_API int cfgpp_op_linear(const void* a, int lda, const void* a2, int lda2, 
   });
 }
 
+// Debug aid (not in the public header): run the linear op `iters` times and return per-CTA timestamps of the last run.
+CFGPP_API int cfgpp_dbg_linear_timeline(const void* a, int lda, const void* w, int M, int N, int K, const void* bias,
+                                        const void* addend, void* out, int force_bn, int iters,
+                                        unsigned long long* host_out /*[grid][16]*/, int* grid_out, void* stream) {
+  return guarded([&] {
+    GemmOp op = make_linear_op((const __half*)a, lda, nullptr, 0, 0, (const __half*)w, M, N, K, (const __half*)bias,
+                               (const __half*)addend, N, 1, (__half*)out, N, false, force_bn);
+    unsigned long long* d = nullptr;
+    CFGPP_CHECK_CUDA(cudaMalloc(&d, sizeof(unsigned long long) * 16 * op.grid));
+    CFGPP_CHECK_CUDA(cudaMemset(d, 0, sizeof(unsigned long long) * 16 * op.grid));
+    op.p.timeline = d;
+    for (int i = 0; i < iters; ++i) run_gemm_op(op, (cudaStream_t)stream);
+    CFGPP_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    CFGPP_CHECK_CUDA(cudaMemcpy(host_out, d, sizeof(unsigned long long) * 16 * op.grid, cudaMemcpyDeviceToHost));
+    *grid_out = op.grid;
+    cudaFree(d);
+  });
+}
+
 CFGPP_API int cfgpp_op_conv3x3(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias,
                                const void* addend, int ld_add, int add_rows_per_group, void* out, int force_bn,
                                void* stream) {

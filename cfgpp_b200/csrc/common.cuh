@@ -289,6 +289,12 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N, ui
 // ----------------------------------------------------------------------------------------------
 // misc math
 // ----------------------------------------------------------------------------------------------
+CFGPP_DEVICE unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 CFGPP_DEVICE float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 CFGPP_DEVICE float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 

@@ -35,7 +35,9 @@ struct Cfg {
       CL == 2 ? (GEGLU ? 6 : (BN == 256 ? 5 : 6)) : (GEGLU ? 4 : (BN == 256 ? 3 : (BN == 160 ? 5 : 6)));
   static constexpr int TMEM_COLS = (BN <= 64) ? 128 : (BN <= 128 ? 256 : 512);
   static constexpr int ACC_STRIDE = TMEM_COLS / 2;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int VEC_BYTES = 2 * 256 * 2;  // per-tile bias and time-embedding row staged for the epilogue
+  static constexpr int SMEM_BYTES =
+      STAGES * STAGE_BYTES + EPI_BYTES + VEC_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of an SM");
 };
 
@@ -58,7 +60,9 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
   uint8_t* epi_smem = smem + C::STAGES * C::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + C::EPI_BYTES);
+  __half* s_bias = reinterpret_cast<__half*>(epi_smem + C::EPI_BYTES);  // [256]
+  __half* s_temb = s_bias + 256;                                         // [256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + C::EPI_BYTES + C::VEC_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::STAGES;
   uint64_t* tmem_full_bar = bars + 2 * C::STAGES;
@@ -68,6 +72,9 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  unsigned long long* tl = p.timeline ? p.timeline + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
+#define TL(slot) do { if (tl) tl[slot] = globaltimer_ns(); } while (0)
+  if (threadIdx.x == 0) TL(0);
   const int cta_rank = (CL > 1) ? static_cast<int>(cluster_ctarank()) : 0;
   const int cluster_id = blockIdx.x / CL;
   const int num_clusters = gridDim.x / CL;
@@ -107,8 +114,10 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
   if constexpr (CL > 1) cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) TL(1);
   pdl_launch_dependents();  // the next kernel may start its prologue on SMs this grid leaves
   pdl_wait();               // everything above overlapped the previous kernel's tail; its outputs are needed below
+  if (threadIdx.x == 0) TL(2);
 
   // tiles are enumerated as (m-group, n) with CL vertically adjacent M blocks per group; a cluster walks the groups,
   // CTA `cta_rank` takes M block  group * CL + cta_rank  (possibly a phantom block past M: loads zero-fill, stores clip)
@@ -137,6 +146,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
         }
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (tile == cluster_id && kb == 0) TL(3);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           if constexpr (CL == 1) {
@@ -193,6 +203,9 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
         const uint32_t d_tmem = tmem_base + as * C::ACC_STRIDE;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          if (it == 0 && kb == 0) TL(4);
+          if (it == 0 && kb == nkb - 1) TL(5);
+          if (kb == nkb - 1) TL(6);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_BYTES;
@@ -249,15 +262,33 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
       const int m_blk = tile_m_blk(tile);
       const int n_blk = tile_n_blk(tile);
       const int m = m_blk * BM + row;
-      mbar_wait(&tmem_full_bar[as], aph);
-      tc_fence_after();
-      if (full_res) mbar_wait(res_full_bar, it & 1);
-      const uint32_t t_base = tmem_base + as * C::ACC_STRIDE + lane_off;
+      // Stage this tile's bias (and, when all 128 rows belong to one sample, its time-embedding row) in shared memory
+      // while the main loop is still running: global loads inside the per-chunk loop would expose ~1 us each.
       const __half* add_row = nullptr;  // per-sample row broadcast (ResnetBlock2D time embedding)
+      bool temb_staged = false;
       if (p.addend != nullptr && !full_res) {
+        const int m_first = m_blk * BM;
+        const int m_last = (m_first + BM - 1 < p.M ? m_first + BM - 1 : p.M - 1);
+        temb_staged = (m_first < p.M) && (m_first / p.add_rows_per_group == m_last / p.add_rows_per_group);
         const int mm = m < p.M ? m : p.M - 1;
         add_row = p.addend + static_cast<size_t>(mm / p.add_rows_per_group) * p.ld_add;
       }
+      {
+        const int ncols = GEGLU ? BN : C::OUT_N;  // GEGLU stages value + gate biases (packed alike)
+        const int n_base = n_blk * BN;
+        for (int c = row; c < ncols; c += 128) {
+          const int n = n_base + c;
+          const bool ok = n < p.N;
+          if (p.bias) s_bias[c] = ok ? p.bias[n] : __float2half(0.f);
+          if (temb_staged) s_temb[c] = ok ? add_row[n] : __float2half(0.f);
+        }
+      }
+      mbar_wait(&tmem_full_bar[as], aph);
+      if (leader) { if (it == 0) TL(7); TL(9); if (tl) tl[12] = it + 1; }
+      tc_fence_after();
+      if (full_res) mbar_wait(res_full_bar, it & 1);
+      named_bar_sync(1, 128);  // staged vectors visible to all epilogue threads
+      const uint32_t t_base = tmem_base + as * C::ACC_STRIDE + lane_off;
 
       if constexpr (!GEGLU) {
 #pragma unroll 1
@@ -267,7 +298,6 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
           tmem_ld_wait();
           const int n0 = n_blk * BN + j * 32;
           uint8_t* srow = my_row + j * C::EPI_SUB_BYTES;
-          const bool cols_ok = (n0 + 32 <= p.N);
           uint32_t o[16];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -279,25 +309,20 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
               const int jj = c * 4 + e;  // half2 index within the 32-column chunk
               float x0 = __uint_as_float(v[2 * jj]), x1 = __uint_as_float(v[2 * jj + 1]);
               if (p.bias) {
-                if (cols_ok) {
-                  const __half2 b = *reinterpret_cast<const __half2*>(p.bias + n0 + 2 * jj);
-                  x0 += __low2float(b);
-                  x1 += __high2float(b);
-                } else {
-                  if (n0 + 2 * jj < p.N) x0 += __half2float(p.bias[n0 + 2 * jj]);
-                  if (n0 + 2 * jj + 1 < p.N) x1 += __half2float(p.bias[n0 + 2 * jj + 1]);
-                }
+                const __half2 b = *reinterpret_cast<const __half2*>(s_bias + j * 32 + 2 * jj);
+                x0 += __low2float(b);
+                x1 += __high2float(b);
               }
               __half2 t = __floats2half2_rn(x0, x1);
               if (full_res) {
                 t = __floats2half2_rn(__low2float(t) + __low2float(rh[e]), __high2float(t) + __high2float(rh[e]));
               } else if (add_row) {
                 float a0 = 0.f, a1 = 0.f;
-                if (cols_ok) {
-                  const __half2 a = *reinterpret_cast<const __half2*>(add_row + n0 + 2 * jj);
+                if (temb_staged) {
+                  const __half2 a = *reinterpret_cast<const __half2*>(s_temb + j * 32 + 2 * jj);
                   a0 = __low2float(a);
                   a1 = __high2float(a);
-                } else {
+                } else {  // tile spans several samples (tiny latents): per-row global loads
                   if (n0 + 2 * jj < p.N) a0 = __half2float(add_row[n0 + 2 * jj]);
                   if (n0 + 2 * jj + 1 < p.N) a1 = __half2float(add_row[n0 + 2 * jj + 1]);
                 }
@@ -316,8 +341,6 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
           tmem_ld_x32(t_base + j * 32, va);
           tmem_ld_x32(t_base + BN / 2 + j * 32, vg);
           tmem_ld_wait();
-          const int na = n_blk * BN + j * 32;  // packed-row index of the value half (bias is packed alike)
-          const int ng = na + BN / 2;
           uint8_t* srow = my_row + j * C::EPI_SUB_BYTES;
           uint32_t o[16];
 #pragma unroll
@@ -325,8 +348,8 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
             float a0 = __uint_as_float(va[2 * jj]), a1 = __uint_as_float(va[2 * jj + 1]);
             float g0 = __uint_as_float(vg[2 * jj]), g1 = __uint_as_float(vg[2 * jj + 1]);
             if (p.bias) {
-              const __half2 ba = *reinterpret_cast<const __half2*>(p.bias + na + 2 * jj);
-              const __half2 bg = *reinterpret_cast<const __half2*>(p.bias + ng + 2 * jj);
+              const __half2 ba = *reinterpret_cast<const __half2*>(s_bias + j * 32 + 2 * jj);
+              const __half2 bg = *reinterpret_cast<const __half2*>(s_bias + BN / 2 + j * 32 + 2 * jj);
               a0 += __low2float(ba);
               a1 += __high2float(ba);
               g0 += __low2float(bg);
@@ -353,6 +376,8 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
         for (int j = 0; j < C::EPI_SUB; ++j)
           tma_store_2d(&map_out, epi_smem + j * C::EPI_SUB_BYTES, n_blk * C::OUT_N + j * 32, m_blk * BM);
         tma_store_commit();
+        if (it == 0) TL(8);
+        TL(10);
         tma_store_wait_read0();  // staging tile has been read out: reusable
         const int next = tile + num_clusters;
         if (full_res && next < num_tiles) issue_residual(next);
@@ -360,6 +385,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
       named_bar_sync(1, 128);
     }
     if (leader) tma_store_wait0();
+    if (leader) TL(11);
   }
 
   tc_fence_before();

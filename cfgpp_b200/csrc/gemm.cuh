@@ -34,6 +34,7 @@ struct GemmParams {
   __half* out;
   int ldc;
   int geglu;
+  unsigned long long* timeline;  // debug: per-CTA timestamps (16 slots each), nullptr in production
 };
 
 struct GemmOp {
