@@ -4,9 +4,10 @@
 // both query tiles share (K / V are fetched once per pair):
 //   warp 0 lane 0 : TMA producer (Q0, Q1 once; K / V rings, 128B swizzle)
 //   warp 1 lane 0 : MMA issuer   S_q = Q_q K_j^T   (M128 N128 K64, fp32 in TMEM)
-//                                O_q += P_q V_j    (M128 N64 K128; A = P from swizzled smem, B = V MN-major),
-//                   interleaved  PV_0(j) QK_0(j+1) PV_1(j) QK_1(j+1)  so the tensor pipe works for one query tile
-//                   while the softmax warps of the other are busy
+//                                O_q += P_q V_j    (M128 N64 K128; A = P from swizzled smem, B = V MN-major).
+//                   Event driven: QK_q(j+1) is issued as soon as the softmax warps of q have pulled S_q(j) into
+//                   registers (s_free), PV_q(j) as soon as P_q(j) is in shared memory (p_full) — whichever comes
+//                   first — so neither query tile's softmax ever waits for the tensor pipe
 //   warp 2        : TMEM allocator (512 columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384))
 //   warps 4..7    : softmax of query tile 0, warps 8..11: query tile 1 — one row per thread:
 //                   a single TMEM read of the 128 scores into registers, row max, p = exp2((s - m) * scale*log2e),
@@ -51,7 +52,8 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
   uint64_t* v_full = k_empty + KS;
   uint64_t* v_empty = v_full + KS;
   uint64_t* s_full = v_empty + KS;    // [2]
-  uint64_t* p_full = s_full + 2;      // [2]
+  uint64_t* s_free = s_full + 2;      // [2]
+  uint64_t* p_full = s_free + 2;      // [2]
   uint64_t* pv_done = p_full + 2;     // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pv_done + 2);
 
@@ -72,14 +74,15 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 128);
       mbar_init(&p_full[i], 128);
       mbar_init(&pv_done[i], 1);
     }
     for (int i = 0; i < KS; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
+      mbar_init(&k_empty[i], n_qt);  // one tcgen05.commit per query tile that consumed the stage
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&v_empty[i], n_qt);
     }
     fence_barrier_init();
   }
@@ -140,21 +143,41 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
       for (int qt = 0; qt < n_qt; ++qt) mbar_wait(&q_full[qt], 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      for (int qt = 0; qt < n_qt; ++qt) issue_qk(qt, 0);
-      umma_commit(&k_empty[0]);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int sv = j % KS;
-        mbar_wait(&v_full[sv], (j / KS) & 1);
-        const bool more = (j + 1 < n_tiles);
-        if (more) mbar_wait(&k_full[(j + 1) % KS], ((j + 1) / KS) & 1);
+      for (int qt = 0; qt < n_qt; ++qt) {
+        issue_qk(qt, 0);
+        umma_commit(&k_empty[0]);
+      }
+      int next_qk[2] = {1, 1}, next_pv[2] = {0, 0};
+      int remaining = n_qt * (2 * n_tiles - 1);
+      long long t_start = clock64();
+      while (remaining > 0) {
+        bool progressed = false;
         for (int qt = 0; qt < n_qt; ++qt) {
-          mbar_wait(&p_full[qt], j & 1);  // P_q(j) written (implies S_q(j) consumed and any O_q rescale finished)
-          tc_fence_after();
-          issue_pv(qt, j);
-          if (more) issue_qk(qt, j + 1);
+          int j = next_pv[qt];
+          if (j < n_tiles && mbar_try_wait(&p_full[qt], j & 1) && mbar_try_wait(&v_full[j % KS], (j / KS) & 1)) {
+            tc_fence_after();
+            issue_pv(qt, j);
+            umma_commit(&v_empty[j % KS]);
+            ++next_pv[qt];
+            --remaining;
+            progressed = true;
+          }
+          j = next_qk[qt];
+          if (j < n_tiles && mbar_try_wait(&s_free[qt], (j - 1) & 1) && mbar_try_wait(&k_full[j % KS], (j / KS) & 1)) {
+            tc_fence_after();
+            issue_qk(qt, j);
+            umma_commit(&k_empty[j % KS]);
+            ++next_qk[qt];
+            --remaining;
+            progressed = true;
+          }
         }
-        umma_commit(&v_empty[sv]);
-        if (more) umma_commit(&k_empty[(j + 1) % KS]);
+        if (progressed) {
+          t_start = clock64();
+        } else if (clock64() - t_start > 4000000000LL) {
+          printf("cfgpp: attention MMA issuer stalled (block %d,%d,%d)\n", blockIdx.x, blockIdx.y, blockIdx.z);
+          __trap();
+        }
       }
     }
   } else if (warp_idx >= 4) {
@@ -178,6 +201,8 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
 #pragma unroll
         for (int g = 0; g < 4; ++g) tmem_ld_x32(s_addr + g * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[g * 32]));
         tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_free[qt]);  // scores are in registers: the tensor pipe may already produce S_q(j+1)
         if (valid < BKV) {
 #pragma unroll
           for (int i = 0; i < 128; ++i)

@@ -112,6 +112,8 @@ __global__ void conv_in_kernel(const void* __restrict__ z, int z_is_half, const 
                                int B, int H, int W, int Cout, int reps, int px_per_block) {
   pdl_launch_dependents();
   pdl_wait();
+  // thread = (group of 4 horizontally adjacent pixels, 8 output channels): the 4 x 3 x 6 input patch is loaded once
+  // and every weight fetched from shared memory feeds 4 pixels.
   extern __shared__ float sw[];  // [36][Cout] fp32 (tap-major: ci*9 + kh*3 + kw), then bias [Cout]
   const int use_scale = in_scale_ptr != nullptr;
   const float in_scale = use_scale ? *in_scale_ptr : 1.0f;
@@ -124,49 +126,67 @@ __global__ void conv_in_kernel(const void* __restrict__ z, int z_is_half, const 
   const int ocg_n = Cout >> 3;
   const int HW = H * W;
   const int total = B * HW;
-  for (int li = threadIdx.x; li < px_per_block * ocg_n; li += blockDim.x) {
-    const int pix = blockIdx.x * px_per_block + li / ocg_n;
+  const int Wq = W >> 2;  // pixel quads per row (W % 4 == 0)
+  for (int li = threadIdx.x; li < (px_per_block >> 2) * ocg_n; li += blockDim.x) {
+    const int quad = blockIdx.x * (px_per_block >> 2) + li / ocg_n;
     const int ocg = li % ocg_n;
-    if (pix >= total) break;
-    const int b = pix / HW;
-    const int r = pix - b * HW;
-    const int h = r / W, x = r - h * W;
-    float acc[8];
+    if (quad * 4 >= total) break;
+    const int b = quad / (H * Wq);
+    const int r = quad - b * (H * Wq);
+    const int h = r / Wq, x0 = (r - h * Wq) * 4;
+    float acc[4][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = sw[36 * Cout + ocg * 8 + i];
+    for (int px = 0; px < 4; ++px)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[px][i] = sw[36 * Cout + ocg * 8 + i];
 #pragma unroll
     for (int ci = 0; ci < 4; ++ci) {
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
+        const int hh = h + kh - 1;
+        float v[6];
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const int hh = h + kh - 1, ww = x + kw - 1;
-          float v = 0.f;
+        for (int c = 0; c < 6; ++c) {
+          const int ww = x0 + c - 1;
+          float val = 0.f;
           if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
             const size_t off = (static_cast<size_t>(b) * 4 + ci) * HW + hh * W + ww;
             if (z_is_half) {
               __half hv = reinterpret_cast<const __half*>(z)[off];
               if (use_scale) hv = __float2half_rn(__half2float(hv) * in_scale);  // x * c_in in fp16 arithmetic
-              v = __half2float(hv);
+              val = __half2float(hv);
             } else {
               float fv = reinterpret_cast<const float*>(z)[off];
               if (use_scale) fv = fv * in_scale;
-              v = __half2float(__float2half_rn(fv));  // autocast: conv input cast to fp16
+              val = __half2float(__float2half_rn(fv));  // autocast: conv input cast to fp16
             }
           }
-          const float* wt = sw + (ci * 9 + kh * 3 + kw) * Cout + ocg * 8;
+          v[c] = val;
+        }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] += v * wt[i];
+        for (int kw = 0; kw < 3; ++kw) {
+          const float* wt = sw + (ci * 9 + kh * 3 + kw) * Cout + ocg * 8;
+          float wv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) wv[i] = wt[i];
+#pragma unroll
+          for (int px = 0; px < 4; ++px)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[px][i] += v[px + kw] * wv[i];
         }
       }
     }
-    uint4 o;
-    o.x = pack_half2(acc[0], acc[1]);
-    o.y = pack_half2(acc[2], acc[3]);
-    o.z = pack_half2(acc[4], acc[5]);
-    o.w = pack_half2(acc[6], acc[7]);
-    for (int rep = 0; rep < reps; ++rep)
-      *reinterpret_cast<uint4*>(out + (static_cast<size_t>(rep) * total + pix) * Cout + ocg * 8) = o;
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      uint4 o;
+      o.x = pack_half2(acc[px][0], acc[px][1]);
+      o.y = pack_half2(acc[px][2], acc[px][3]);
+      o.z = pack_half2(acc[px][4], acc[px][5]);
+      o.w = pack_half2(acc[px][6], acc[px][7]);
+      const size_t pix = static_cast<size_t>(b) * HW + h * W + x0 + px;
+      for (int rep = 0; rep < reps; ++rep)
+        *reinterpret_cast<uint4*>(out + (static_cast<size_t>(rep) * total + pix) * Cout + ocg * 8) = o;
+    }
   }
 }
 
@@ -395,8 +415,8 @@ void run_select_step(const StepState* table, int* counter, StepState* cur, cudaS
 
 void run_conv_in(const void* z, int z_is_half, const float* in_scale, const __half* w, const __half* bias,
                  __half* out, int B, int H, int W, int Cout, int reps, cudaStream_t stream) {
-  CFGPP_REQUIRE(Cout % 8 == 0, "conv_in Cout must be a multiple of 8");
-  const int ppb = 32;
+  CFGPP_REQUIRE(Cout % 8 == 0 && W % 4 == 0, "conv_in needs Cout % 8 == 0 and W % 4 == 0");
+  const int ppb = 128;
   const size_t smem = (36 * Cout + Cout) * sizeof(float);
   static bool configured = false;
   if (!configured && smem > 48 * 1024) {

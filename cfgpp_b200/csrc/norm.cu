@@ -242,7 +242,12 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, int M, int C, con
 
 }  // namespace
 
-int gn_px_per_block(int HW) { return HW <= 4096 ? 64 : 128; }
+// up to 128 pixel chunks per sample (the partial-sum buffer holds 128) so that even the 32x32 level launches
+// >= 512 blocks; at least 4 pixels per block
+int gn_px_per_block(int HW) {
+  int ppb = (HW + 127) / 128;
+  return ppb < 4 ? 4 : ppb;
+}
 int gn_num_chunks(int HW) { return (HW + gn_px_per_block(HW) - 1) / gn_px_per_block(HW); }
 size_t gn_partial_floats(int B, int HW) { return static_cast<size_t>(B) * gn_num_chunks(HW) * GROUPS * 2; }
 
