@@ -87,8 +87,9 @@ def op_conv3x3(x_nhwc: torch.Tensor, w_packed: torch.Tensor, bias=None, addend=N
     return out
 
 
-def op_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int) -> torch.Tensor:
-    """q [B,Nq,H*64], k/v [B,Nkv,H*64] fp16 (views with a row stride are fine) -> [B,Nq,H*64]."""
+def op_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, head_dim: int = 64) -> torch.Tensor:
+    """q [B,Nq,H*P], k/v [B,Nkv,H*P] fp16 (views with a row stride are fine) -> [B,Nq,H*P]; P = head_dim rounded up
+    to a multiple of 64, the padding columns of every head being zero."""
     lib = load()
     B, Nq, C = q.shape
     Nkv = k.shape[1]
@@ -97,7 +98,7 @@ def op_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int) 
         assert t.is_cuda and t.stride(2) == 1 and t.stride(0) == t.shape[1] * t.stride(1)
     check(lib.cfgpp_op_attention(c_void_p(q.data_ptr()), c_int(q.stride(1)), c_void_p(k.data_ptr()), c_int(k.stride(1)),
                                  c_void_p(v.data_ptr()), c_int(v.stride(1)), ptr(out), c_int(C), c_int(B),
-                                 c_int(heads), c_int(Nq), c_int(Nkv), stream_ptr()))
+                                 c_int(heads), c_int(Nq), c_int(Nkv), c_int(head_dim), stream_ptr()))
     return out
 
 

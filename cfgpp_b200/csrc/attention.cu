@@ -15,6 +15,8 @@
 //                   max is only advanced (and O / l rescaled, through tcgen05.ld/st) when the new maximum exceeds
 //                   the reference by more than 2^8 in the exp2 domain — exact after the final 1/l normalisation,
 //                   and p <= 256 stays well inside fp16 / fp32 range.
+#include <cmath>
+
 #include "attention.cuh"
 #include "common.cuh"
 
@@ -26,26 +28,40 @@ namespace {
 
 constexpr int BQ = 128;
 constexpr int BKV = 128;
-constexpr int HD = 64;
-constexpr int KS = 3;                     // K / V ring depth
-constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KB: Q, K, V tiles and each 64-column half of a P tile
-constexpr int SMEM_BYTES = TILE_BYTES * (2 + 2 * KS + 4) + 1024 + 256;
+constexpr int ATOM_BYTES = 128 * 64 * 2;  // 16 KB: one [128 rows x 64 fp16] swizzle-128B atom
 constexpr int kThreads = 384;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t O_COL = 256;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
+// HD = padded head dim (64 / 128 / 192: heads of 40 / 80 / 160 channels are zero-padded by the QKV projection),
+// NQT = query tiles per CTA, KS = K / V ring depth. TMEM: S_q at [q*128], O_q at [NQT*128 + q*HD].
+template <int HD, int NQT, int KS>
+struct ACfg {
+  static constexpr int NA = HD / 64;                    // swizzle atoms per tile row
+  static constexpr int TILE_BYTES = NA * ATOM_BYTES;    // one Q / K / V tile
+  static constexpr int P_BYTES = 2 * ATOM_BYTES;        // one P tile (128 x 128 fp16)
+  static constexpr int SMEM_BYTES = TILE_BYTES * (NQT + 2 * KS) + P_BYTES * NQT + 1024 + 256;
+  static constexpr uint32_t O_COL = NQT * 128;
+  static_assert(NQT * 128 + NQT * HD <= 512, "TMEM overflow");
+  static_assert(SMEM_BYTES <= 232448, "shared memory overflow");
+};
+
+template <int HD, int NQT, int KS>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
             const __grid_constant__ CUtensorMap map_v) {
+  using A = ACfg<HD, NQT, KS>;
+  constexpr int TILE_BYTES = A::TILE_BYTES;
+  constexpr int NA = A::NA;
+  constexpr uint32_t O_COL = A::O_COL;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint8_t* sQ = smem;                      // 2 tiles
-  uint8_t* sK = sQ + 2 * TILE_BYTES;       // KS tiles
+  uint8_t* sQ = smem;                      // NQT tiles
+  uint8_t* sK = sQ + NQT * TILE_BYTES;     // KS tiles
   uint8_t* sV = sK + KS * TILE_BYTES;      // KS tiles
-  uint8_t* sP = sV + KS * TILE_BYTES;      // 2 query tiles x 2 halves
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * TILE_BYTES);
+  uint8_t* sP = sV + KS * TILE_BYTES;      // NQT query tiles x 2 halves of 64 columns
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NQT * A::P_BYTES);
   uint64_t* q_full = bars;            // [2]
   uint64_t* k_full = q_full + 2;      // [KS]
   uint64_t* k_empty = k_full + KS;
@@ -59,11 +75,11 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 2 * BQ;
+  const int q0 = blockIdx.x * NQT * BQ;
   const int head = blockIdx.y;
   const int batch = blockIdx.z;
   const int n_tiles = (p.Nkv + BKV - 1) / BKV;
-  const int n_qt = (q0 + BQ < p.Nq) ? 2 : 1;  // query tiles handled by this CTA
+  const int n_qt = (NQT == 2 && q0 + BQ < p.Nq) ? 2 : 1;  // query tiles handled by this CTA
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&map_q);
@@ -102,17 +118,21 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
       // ===================== TMA producer =====================
       for (int qt = 0; qt < n_qt; ++qt) {
         mbar_arrive_expect_tx(&q_full[qt], TILE_BYTES);
-        tma_load_3d(sQ + qt * TILE_BYTES, &map_q, &q_full[qt], head * HD, q0 + qt * BQ, batch);
+        for (int a = 0; a < NA; ++a)
+          tma_load_3d(sQ + qt * TILE_BYTES + a * ATOM_BYTES, &map_q, &q_full[qt], head * HD + a * 64, q0 + qt * BQ,
+                      batch);
       }
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j % KS;
         const uint32_t ph = (j / KS) & 1;
         mbar_wait(&k_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
-        tma_load_3d(sK + s * TILE_BYTES, &map_k, &k_full[s], head * HD, j * BKV, batch);
+        for (int a = 0; a < NA; ++a)
+          tma_load_3d(sK + s * TILE_BYTES + a * ATOM_BYTES, &map_k, &k_full[s], head * HD + a * 64, j * BKV, batch);
         mbar_wait(&v_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
-        tma_load_3d(sV + s * TILE_BYTES, &map_v, &v_full[s], head * HD, j * BKV, batch);
+        for (int a = 0; a < NA; ++a)
+          tma_load_3d(sV + s * TILE_BYTES + a * ATOM_BYTES, &map_v, &v_full[s], head * HD + a * 64, j * BKV, batch);
       }
     }
   } else if (warp_idx == 1) {
@@ -121,21 +141,24 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
       constexpr uint32_t idesc_qk = make_idesc_f16(128, BKV, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_f16(128, HD, 0, 1);  // B (= V) is MN-major
       auto issue_qk = [&](int qt, int j) {
-        const uint64_t q_desc = make_sdesc_sw128(smem_u32(sQ + qt * TILE_BYTES), 1024, 0);
-        const uint64_t k_desc = make_sdesc_sw128(smem_u32(sK + (j % KS) * TILE_BYTES), 1024, 0);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_f16(tmem_base + qt * BKV, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+        for (int a = 0; a < NA; ++a) {  // K dimension = head dim: one 64-wide swizzle atom at a time
+          const uint64_t q_desc = make_sdesc_sw128(smem_u32(sQ + qt * TILE_BYTES + a * ATOM_BYTES), 1024, 0);
+          const uint64_t k_desc = make_sdesc_sw128(smem_u32(sK + (j % KS) * TILE_BYTES + a * ATOM_BYTES), 1024, 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base + qt * BKV, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, (a | k) != 0 ? 1u : 0u);
+        }
         umma_commit(&s_full[qt]);
       };
       auto issue_pv = [&](int qt, int j) {
-        // V tile: 128 kv rows x 64 d (128 B per row, swizzled) = MN-major B operand with a single 64-wide MN atom:
-        // 8-row K groups are 1024 B apart (SBO); a K step of 16 rows advances 2048 B.
-        const uint64_t v_desc = make_sdesc_sw128(smem_u32(sV + (j % KS) * TILE_BYTES), 1024, TILE_BYTES);
+        // V tile: 128 kv rows x HD d as NA atoms of [128 rows x 64 d] (128 B per row, swizzled) = MN-major B operand:
+        // 8-row K groups are 1024 B apart (SBO), 64-wide N atoms 16 KB apart (LBO); a K step of 16 rows advances 2048 B.
+        const uint64_t v_desc = make_sdesc_sw128(smem_u32(sV + (j % KS) * TILE_BYTES), 1024, ATOM_BYTES);
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
           const uint64_t p_desc =
-              make_sdesc_sw128(smem_u32(sP + (2 * qt + (k >> 2)) * TILE_BYTES), 1024, 0) + 2 * (k & 3);
+              make_sdesc_sw128(smem_u32(sP + qt * A::P_BYTES + (k >> 2) * ATOM_BYTES), 1024, 0) + 2 * (k & 3);
           umma_f16(tmem_base + O_COL + qt * HD, p_desc, v_desc + 128 * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
         }
         umma_commit(&pv_done[qt]);
@@ -189,7 +212,7 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
       const uint32_t lane_off = static_cast<uint32_t>(qw * 32) << 16;
       const uint32_t s_addr = tmem_base + qt * BKV + lane_off;
       const uint32_t o_addr = tmem_base + O_COL + qt * HD + lane_off;
-      uint8_t* prow = sP + 2 * qt * TILE_BYTES + row * 128;
+      uint8_t* prow = sP + qt * A::P_BYTES + row * 128;
       const float c = p.scale_log2e;
       float m_ref = -INFINITY, l_run = 0.f;
 
@@ -230,7 +253,7 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
           tc_fence_after();
           if (__any_sync(0xffffffffu, need)) {
 #pragma unroll 1
-            for (int h = 0; h < 4; ++h) {  // 16 columns at a time: the 128 scores stay live in registers
+            for (int h = 0; h < HD / 16; ++h) {  // 16 columns at a time: the 128 scores stay live in registers
               uint32_t o[16];
               tmem_ld_x16(o_addr + h * 16, o);
               tmem_ld_wait();
@@ -257,7 +280,7 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
           }
           const int half_idx = g >> 3;        // which 64-column half
           const int ch = (g & 7) ^ (row & 7);  // 128B swizzle
-          *reinterpret_cast<uint4*>(prow + half_idx * TILE_BYTES + ch * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(prow + half_idx * ATOM_BYTES + ch * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
         l_run += rs0 + rs1;
         tc_fence_before();
@@ -269,8 +292,8 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
       const float inv_l = 1.0f / l_run;
       const int qrow = q0 + qt * BQ + row;
       __half* dst = p.out + (static_cast<size_t>(batch) * p.Nq + qrow) * p.ldo + head * HD;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
+#pragma unroll 1
+      for (int h = 0; h < HD / 32; ++h) {
         uint32_t o[32];
         tmem_ld_x32(o_addr + h * 32, o);
         tmem_ld_wait();
@@ -304,32 +327,57 @@ CUtensorMap make_head_map(const __half* base, int ld, int B, int N, int cols) {
   return make_tmap_f16(base, 3, dims, strides, box);
 }
 
+template <int HD, int NQT, int KS>
+void configure_one() {
+  CFGPP_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel<HD, NQT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        ACfg<HD, NQT, KS>::SMEM_BYTES));
+}
+
+template <int HD, int NQT, int KS>
+void launch(const AttnOp& op, cudaStream_t stream) {
+  dim3 grid((op.p.Nq + NQT * BQ - 1) / (NQT * BQ), op.p.H, op.p.B);
+  launch_pdl(attn_kernel<HD, NQT, KS>, grid, dim3(kThreads), ACfg<HD, NQT, KS>::SMEM_BYTES, stream, op.p, op.map_q,
+             op.map_k, op.map_v);
+}
+
 }  // namespace
 
+int attn_padded_head_dim(int head_dim) { return ((head_dim + 63) / 64) * 64; }
+
 AttnOp make_attn_op(const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, __half* out,
-                    int ldo, int B, int H, int Nq, int Nkv) {
+                    int ldo, int B, int H, int Nq, int Nkv, int head_dim) {
   AttnOp op{};
   CFGPP_REQUIRE(Nkv >= 1 && Nq >= 1, "empty attention");
   CFGPP_REQUIRE(ldo % 8 == 0, "ldo must be a multiple of 8");
+  CFGPP_REQUIRE(head_dim >= 8 && head_dim <= 192, "attention supports head_dim <= 192");
+  const int hdp = attn_padded_head_dim(head_dim);
+  op.hd_pad = hdp;
+  op.head_dim = head_dim;
   op.p.B = B; op.p.H = H; op.p.Nq = Nq; op.p.Nkv = Nkv; op.p.ldo = ldo; op.p.out = out;
-  op.p.scale_log2e = 0.125f * 1.4426950408889634f;
-  op.map_q = make_head_map(q, ldq, B, Nq, H * HD);
-  op.map_k = make_head_map(k, ldk, B, Nkv, H * HD);
-  op.map_v = make_head_map(v, ldv, B, Nkv, H * HD);
+  op.p.scale_log2e = (1.0f / sqrtf(static_cast<float>(head_dim))) * 1.4426950408889634f;
+  op.map_q = make_head_map(q, ldq, B, Nq, H * hdp);
+  op.map_k = make_head_map(k, ldk, B, Nkv, H * hdp);
+  op.map_v = make_head_map(v, ldv, B, Nkv, H * hdp);
   return op;
 }
 
 void attn_configure() {
   static bool done = false;
   if (done) return;
-  CFGPP_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  configure_one<64, 2, 3>();
+  configure_one<128, 1, 2>();
+  configure_one<192, 1, 1>();
   done = true;
 }
 
 void run_attn_op(const AttnOp& op, cudaStream_t stream) {
   attn_configure();
-  dim3 grid((op.p.Nq + 2 * BQ - 1) / (2 * BQ), op.p.H, op.p.B);
-  launch_pdl(attn_kernel, grid, dim3(kThreads), SMEM_BYTES, stream, op.p, op.map_q, op.map_k, op.map_v);
+  switch (op.hd_pad) {
+    case 64: return launch<64, 2, 3>(op, stream);
+    case 128: return launch<128, 1, 2>(op, stream);
+    case 192: return launch<192, 1, 1>(op, stream);
+    default: throw Error(-1, "unsupported padded head dim");
+  }
 }
 
 }  // namespace cfgpp

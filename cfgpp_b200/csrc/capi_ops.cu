@@ -52,10 +52,10 @@ CFGPP_API int cfgpp_op_conv3x3(const void* x, int B, int H, int W, int Cin, cons
 }
 
 CFGPP_API int cfgpp_op_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out,
-                                 int ldo, int B, int H, int Nq, int Nkv, void* stream) {
+                                 int ldo, int B, int H, int Nq, int Nkv, int head_dim, void* stream) {
   return guarded([&] {
     AttnOp op = make_attn_op((const __half*)q, ldq, (const __half*)k, ldk, (const __half*)v, ldv, (__half*)out, ldo,
-                             B, H, Nq, Nkv);
+                             B, H, Nq, Nkv, head_dim);
     run_attn_op(op, (cudaStream_t)stream);
   });
 }

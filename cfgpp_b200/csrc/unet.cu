@@ -43,6 +43,36 @@ __global__ void pack_geglu_kernel(const __half* __restrict__ in, __half* __restr
   }
 }
 
+// rows of `nmat` stacked (heads*hd, K) matrices -> [(mat, head, hdp)][K], rows hd..hdp-1 of every head zero
+__global__ void pack_heads_rows_kernel(const __half* const* __restrict__ mats, __half* __restrict__ out, int nmat,
+                                       int heads, int hd, int hdp, int K) {
+  const size_t n = static_cast<size_t>(nmat) * heads * hdp * K;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int k = i % K;
+    size_t t = i / K;
+    const int r = t % hdp;
+    t /= hdp;
+    const int h = t % heads;
+    const int m = t / heads;
+    out[i] = (r < hd) ? mats[m][(static_cast<size_t>(h) * hd + r) * K + k] : __float2half(0.f);
+  }
+}
+
+// (N, heads*hd) -> (N, heads*hdp) with zero columns hd..hdp-1 per head
+__global__ void pack_heads_cols_kernel(const __half* __restrict__ in, __half* __restrict__ out, int N, int heads, int hd,
+                                       int hdp) {
+  const size_t n = static_cast<size_t>(N) * heads * hdp;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = i % hdp;
+    size_t t = i / hdp;
+    const int h = t % heads;
+    const int row = t / heads;
+    out[i] = (c < hd) ? in[(static_cast<size_t>(row) * heads + h) * hd + c] : __float2half(0.f);
+  }
+}
+
 int grid_for(size_t n) { return static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 8)); }
 
 }  // namespace
@@ -158,6 +188,47 @@ __half* Unet::packed_geglu(const std::string& key, bool is_bias) {
   return out;
 }
 
+__half* Unet::packed_heads_rows(const std::vector<std::string>& keys, int heads, int hd, int hdp) {
+  if (hd == hdp) return keys.size() == 1 ? plain(keys[0]) : packed_cat_rows(keys);
+  std::string name = "heads_rows:";
+  for (auto& k : keys) name += k + "|";
+  auto it = packed_cache_.find(name);
+  if (it != packed_cache_.end()) return it->second;
+  const int K = static_cast<int>(raw(keys[0]).shape[1]);
+  std::vector<const __half*> ptrs;
+  for (auto& k : keys) {
+    const DevTensor& t = raw(k);
+    CFGPP_REQUIRE(t.shape.size() >= 2 && t.shape[0] == heads * hd && t.shape[1] == K, "unexpected projection shape: " + k);
+    ptrs.push_back(t.p);
+  }
+  const __half** dptrs = nullptr;
+  CFGPP_CHECK_CUDA(cudaMalloc(&dptrs, ptrs.size() * sizeof(__half*)));
+  CFGPP_CHECK_CUDA(cudaMemcpy(dptrs, ptrs.data(), ptrs.size() * sizeof(__half*), cudaMemcpyHostToDevice));
+  const size_t total = keys.size() * static_cast<size_t>(heads) * hdp * K;
+  __half* out = alloc_weight(total);
+  pack_heads_rows_kernel<<<grid_for(total), 256>>>(dptrs, out, static_cast<int>(keys.size()), heads, hd, hdp, K);
+  CFGPP_CHECK_CUDA(cudaGetLastError());
+  CFGPP_CHECK_CUDA(cudaDeviceSynchronize());
+  cudaFree(dptrs);
+  packed_cache_[name] = out;
+  return out;
+}
+
+__half* Unet::packed_heads_cols(const std::string& key, int heads, int hd, int hdp) {
+  if (hd == hdp) return plain(key);
+  auto it = packed_cache_.find("heads_cols:" + key);
+  if (it != packed_cache_.end()) return it->second;
+  const DevTensor& t = raw(key);
+  const int N = static_cast<int>(t.shape[0]);
+  CFGPP_REQUIRE(t.shape[1] == heads * hd, "unexpected to_out shape: " + key);
+  const size_t total = static_cast<size_t>(N) * heads * hdp;
+  __half* out = alloc_weight(total);
+  pack_heads_cols_kernel<<<grid_for(total), 256>>>(t.p, out, N, heads, hd, hdp);
+  CFGPP_CHECK_CUDA(cudaGetLastError());
+  packed_cache_["heads_cols:" + key] = out;
+  return out;
+}
+
 void Unet::finalize_weights(cudaStream_t stream) {
   CFGPP_CHECK_CUDA(cudaStreamSynchronize(stream));
   // structural validation: every key the plan will touch must exist (dry walk at a nominal size)
@@ -215,10 +286,10 @@ void Unet::add_step(const std::string& name, std::function<void(cudaStream_t)> f
   cur_plan_->push_back(std::move(s));
 }
 
-void Unet::add_gemm(const std::string& name, const GemmOp& op) {
+void Unet::add_gemm(const std::string& name, const GemmOp& op, double algorithmic_flops) {
   PlanStep s;
   s.name = name;
-  s.flops = op.flops();
+  s.flops = algorithmic_flops >= 0 ? algorithmic_flops : op.flops();
   s.kind = op.p.conv ? 1 : 0;
   s.fn = [op](cudaStream_t st) { run_gemm_op(op, st); };
   cur_plan_->push_back(std::move(s));
@@ -287,13 +358,16 @@ Unet::Act Unet::build_transformer(const std::string& prefix, Act x, int H, int W
   const int Mi = NB_ * HW;
   const size_t M = static_cast<size_t>(Mi);
   const int D = d_.cross_attention_dim;
-  CFGPP_REQUIRE(C % heads == 0 && C / heads == 64,
-                "attention kernel supports head_dim 64 only (got " + std::to_string(C / std::max(heads, 1)) + ") at " + prefix);
+  CFGPP_REQUIRE(C % heads == 0 && C / heads <= 192,
+                "attention supports head_dim <= 192 (got " + std::to_string(C / std::max(heads, 1)) + ") at " + prefix);
+  const int hd = C / heads;
+  const int hdp = attn_padded_head_dim(hd);  // heads are zero-padded to a multiple of 64 channels (SD v1.5: 40/80/160)
+  const int Cp = heads * hdp;
   Scratch* s_norm = scratch("norm", M * C);
   Scratch* s_tok = scratch("tokens", M * C);
-  Scratch* s_qkv = scratch("qkv", M * 3 * C);
-  Scratch* s_attn = scratch("attn", M * C);
-  Scratch* s_q = scratch("q", M * C);
+  Scratch* s_qkv = scratch("qkv", M * 3 * Cp);
+  Scratch* s_attn = scratch("attn", M * Cp);
+  Scratch* s_q = scratch("q", M * Cp);
   Scratch* s_ff = scratch("ff", M * 4 * C);
   __half* out = g_dry ? nullptr : alloc_act(M * C);
   const int Mkv = NB_ * n_ctx_;
@@ -309,7 +383,7 @@ Unet::Act Unet::build_transformer(const std::string& prefix, Act x, int H, int W
                             ".attn2.to_out.0.bias", ".ff.net.0.proj.weight", ".ff.net.0.proj.bias",
                             ".ff.net.2.weight", ".ff.net.2.bias"})
         raw(b + n);
-      workspace_bytes_ += static_cast<size_t>(Mkv) * 2 * C * sizeof(__half);
+      workspace_bytes_ += static_cast<size_t>(Mkv) * 2 * Cp * sizeof(__half);
     }
     workspace_bytes_ += M * C * sizeof(__half);
     return Act{nullptr, C};
@@ -334,28 +408,38 @@ Unet::Act Unet::build_transformer(const std::string& prefix, Act x, int H, int W
     };
     // --- self-attention ---
     add_ln(".norm1");
-    __half* wqkv = packed_cat_rows({b + ".attn1.to_q.weight", b + ".attn1.to_k.weight", b + ".attn1.to_v.weight"});
+    __half* wqkv = packed_heads_rows({b + ".attn1.to_q.weight", b + ".attn1.to_k.weight", b + ".attn1.to_v.weight"},
+                                     heads, hd, hdp);
     add_gemm(b + ".attn1.to_qkv",
-             make_linear_op(normp, C, nullptr, 0, 0, wqkv, Mi, 3 * C, C, nullptr, nullptr, 0, 1, qkv, 3 * C, false));
-    add_attn(b + ".attn1.sdpa", make_attn_op(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, attn, C, NB_, heads, HW, HW));
-    add_gemm(b + ".attn1.to_out", make_linear_op(attn, C, nullptr, 0, 0, plain(b + ".attn1.to_out.0.weight"), Mi, C, C,
-                                                 plain(b + ".attn1.to_out.0.bias"), tok, C, 1, tok, C, false));
+             make_linear_op(normp, C, nullptr, 0, 0, wqkv, Mi, 3 * Cp, C, nullptr, nullptr, 0, 1, qkv, 3 * Cp, false),
+             2.0 * Mi * 3.0 * C * C);
+    add_attn(b + ".attn1.sdpa",
+             make_attn_op(qkv, 3 * Cp, qkv + Cp, 3 * Cp, qkv + 2 * Cp, 3 * Cp, attn, Cp, NB_, heads, HW, HW, hd));
+    add_gemm(b + ".attn1.to_out",
+             make_linear_op(attn, Cp, nullptr, 0, 0, packed_heads_cols(b + ".attn1.to_out.0.weight", heads, hd, hdp), Mi,
+                            C, Cp, plain(b + ".attn1.to_out.0.bias"), tok, C, 1, tok, C, false),
+             2.0 * Mi * static_cast<double>(C) * C);
     // --- cross-attention (K/V projected once per prompt by the prompt plan) ---
     add_ln(".norm2");
-    add_gemm(b + ".attn2.to_q", make_linear_op(normp, C, nullptr, 0, 0, plain(b + ".attn2.to_q.weight"), Mi, C, C,
-                                               nullptr, nullptr, 0, 1, qb, C, false));
-    __half* kv = alloc_act(static_cast<size_t>(Mkv) * 2 * C);
+    add_gemm(b + ".attn2.to_q",
+             make_linear_op(normp, C, nullptr, 0, 0, packed_heads_rows({b + ".attn2.to_q.weight"}, heads, hd, hdp), Mi,
+                            Cp, C, nullptr, nullptr, 0, 1, qb, Cp, false),
+             2.0 * Mi * static_cast<double>(C) * C);
+    __half* kv = alloc_act(static_cast<size_t>(Mkv) * 2 * Cp);
     {
-      __half* wkv = packed_cat_rows({b + ".attn2.to_k.weight", b + ".attn2.to_v.weight"});
+      __half* wkv = packed_heads_rows({b + ".attn2.to_k.weight", b + ".attn2.to_v.weight"}, heads, hd, hdp);
       std::vector<PlanStep>* save = cur_plan_;
       cur_plan_ = &prompt_plan_;
       add_gemm(b + ".attn2.to_kv",
-               make_linear_op(ctx_copy_, D, nullptr, 0, 0, wkv, Mkv, 2 * C, D, nullptr, nullptr, 0, 1, kv, 2 * C, false));
+               make_linear_op(ctx_copy_, D, nullptr, 0, 0, wkv, Mkv, 2 * Cp, D, nullptr, nullptr, 0, 1, kv, 2 * Cp, false),
+               2.0 * Mkv * 2.0 * C * D);
       cur_plan_ = save;
     }
-    add_attn(b + ".attn2.sdpa", make_attn_op(qb, C, kv, 2 * C, kv + C, 2 * C, attn, C, NB_, heads, HW, n_ctx_));
-    add_gemm(b + ".attn2.to_out", make_linear_op(attn, C, nullptr, 0, 0, plain(b + ".attn2.to_out.0.weight"), Mi, C, C,
-                                                 plain(b + ".attn2.to_out.0.bias"), tok, C, 1, tok, C, false));
+    add_attn(b + ".attn2.sdpa", make_attn_op(qb, Cp, kv, 2 * Cp, kv + Cp, 2 * Cp, attn, Cp, NB_, heads, HW, n_ctx_, hd));
+    add_gemm(b + ".attn2.to_out",
+             make_linear_op(attn, Cp, nullptr, 0, 0, packed_heads_cols(b + ".attn2.to_out.0.weight", heads, hd, hdp), Mi,
+                            C, Cp, plain(b + ".attn2.to_out.0.bias"), tok, C, 1, tok, C, false),
+             2.0 * Mi * static_cast<double>(C) * C);
     // --- GEGLU feed-forward ---
     add_ln(".norm3");
     add_gemm(b + ".ff.geglu",

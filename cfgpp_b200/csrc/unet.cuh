@@ -70,6 +70,8 @@ class Unet {
   __half* packed_conv3x3(const std::string& key);  // (Cout,Cin,3,3) -> [Cout][9][Cin]
   __half* packed_cat_rows(const std::vector<std::string>& keys);
   __half* packed_geglu(const std::string& key, bool is_bias);
+  __half* packed_heads_rows(const std::vector<std::string>& keys, int heads, int hd, int hdp);
+  __half* packed_heads_cols(const std::string& key, int heads, int hd, int hdp);
   __half* plain(const std::string& key);
 
   // ---- workspace ----
@@ -88,7 +90,7 @@ class Unet {
   Act build_transformer(const std::string& prefix, Act x, int H, int W, int layers, int heads);
   Act build_downsample(const std::string& prefix, Act x, int H, int W);
   Act build_upsample(const std::string& prefix, Act x, int H, int W);
-  void add_gemm(const std::string& name, const GemmOp& op);
+  void add_gemm(const std::string& name, const GemmOp& op, double algorithmic_flops = -1.0);
   void add_attn(const std::string& name, const AttnOp& op);
   void add_step(const std::string& name, std::function<void(cudaStream_t)> fn, int launches = 1);
   void run_plan(const std::vector<PlanStep>& plan, cudaStream_t stream);

@@ -136,8 +136,10 @@ int cfgpp_op_linear(const void* a, int lda, const void* a2, int lda2, int k_spli
                     int geglu, int force_bn, void* stream);
 int cfgpp_op_conv3x3(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias,
                      const void* addend, int ld_add, int add_rows_per_group, void* out, int force_bn, void* stream);
+/* head h of q / k / v / out occupies columns [h*P, h*P + head_dim) with P = head_dim rounded up to a multiple of 64
+ * (columns head_dim..P-1 must be zero in q / k / v and come back zero in out). */
 int cfgpp_op_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B,
-                       int H, int Nq, int Nkv, void* stream);
+                       int H, int Nq, int Nkv, int head_dim, void* stream);
 int cfgpp_op_groupnorm(const void* x1, int C1, const void* x2, int C2, int B, int HW, const void* gamma,
                        const void* beta, float eps, int silu, void* out, void* stream);
 int cfgpp_op_layernorm(const void* x, int M, int C, const void* gamma, const void* beta, float eps, void* out,

@@ -112,6 +112,27 @@ def test_attention(B, H, Nq, Nkv):
     assert rel_l2(out, ref) < 3e-3
 
 
+@pytest.mark.parametrize("B,H,Nq,Nkv,hd", [(2, 8, 1024, 1024, 80), (1, 8, 4096, 4096, 40), (2, 8, 256, 256, 160),
+                                           (2, 8, 64, 77, 160), (1, 3, 300, 77, 40)])
+def test_attention_padded_heads(B, H, Nq, Nkv, hd):
+    """SD v1.5 head dims (40 / 80 / 160): heads are zero-padded to a multiple of 64 columns in q / k / v."""
+    from cfgpp_b200 import _native as nv
+    g = torch.Generator().manual_seed(hd + Nq)
+    P = (hd + 63) // 64 * 64
+
+    def padded(n):
+        t = torch.zeros(B, n, H, P)
+        t[..., :hd] = torch.randn(B, n, H, hd, generator=g) * 1.1
+        return t.reshape(B, n, H * P).half().to(dev)
+
+    q, k, v = padded(Nq), padded(Nkv), padded(Nkv)
+    out = nv.op_attention(q, k, v, H, head_dim=hd).reshape(B, Nq, H, P)
+    qf, kf, vf = (t.float().reshape(B, -1, H, P)[..., :hd].transpose(1, 2) for t in (q, k, v))
+    ref = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2)
+    assert rel_l2(out[..., :hd], ref) < 3e-3
+    assert out[..., hd:].abs().max() == 0
+
+
 @pytest.mark.parametrize("B,HW,C1,C2,silu,eps", [(2, 1024, 64, 0, True, 1e-5), (4, 16384, 320, 0, True, 1e-5),
                                                  (2, 4096, 640, 320, True, 1e-5), (2, 1024, 1280, 640, False, 1e-6)])
 def test_groupnorm(B, HW, C1, C2, silu, eps):

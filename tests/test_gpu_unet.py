@@ -52,6 +52,12 @@ def test_unet_forward_sdxl_full_size():
     run_case("sdxl", 1, 128, 501)
 
 
+def test_unet_forward_sd15_full_size():
+    """BASELINE configs[0]/[1] geometry: the real SD v1.5 UNet (859.5 M params, head dims 40/80/160, 1x1-conv
+    projections, 8x8 deepest level), 64x64 latent."""
+    run_case("sd15", 1, 64, 401)
+
+
 def test_forward_is_deterministic_and_rows_independent():
     cfg, sd, net, _ = build_pair("tiny_sdxl", dev)
     z, uc, c, add = make_inputs(cfg, 2, 32, dev)

@@ -339,7 +339,7 @@ def diag_unet(which=("tiny_sdxl", "tiny_sd15")):
     from cfgpp_b200.engine import NativeUNet
     from oracle import unet as O
     for name, B, hw, t in [("tiny_sdxl", 2, 32, 801), ("tiny_sd15", 1, 32, 401), ("tiny_sdxl", 1, 64, 21),
-                           ("sdxl", 1, 128, 501)]:
+                           ("sdxl", 1, 128, 501), ("sd15", 1, 64, 401), ("sd15", 2, 64, 981)]:
         if name not in which:
             continue
         label = f"unet {name} B={B} latent={hw} t={t}"
@@ -491,6 +491,8 @@ if __name__ == "__main__":
         diag_unet(("tiny_sdxl", "tiny_sd15"))
     if "unet_sdxl" in which:
         diag_unet(("sdxl",))
+    if "unet_sd15" in which:
+        diag_unet(("sd15",))
     if "bench_unet" in which:
         bench_unet()
     if "prof_unet" in which:
