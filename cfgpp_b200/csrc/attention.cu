@@ -63,8 +63,7 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
   uint8_t* sP = sV + KS * TILE_BYTES;      // NQT query tiles x 2 halves of 64 columns
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NQT * A::P_BYTES);
   uint64_t* q_full = bars;            // [2]
-  uint64_t* q_empty = q_full + 2;     // [2]
-  uint64_t* k_full = q_empty + 2;     // [KS]
+  uint64_t* k_full = q_full + 2;      // [KS]
   uint64_t* k_empty = k_full + KS;
   uint64_t* v_full = k_empty + KS;
   uint64_t* v_empty = v_full + KS;
@@ -76,16 +75,11 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * NQT * BQ;
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
   const int n_tiles = (p.Nkv + BKV - 1) / BKV;
-  // persistent work list: item = (batch, head, group of NQT query tiles); CTA c takes items c, c + grid, ...
-  // Barrier phases run on monotonically increasing counters, so the TMA / MMA / softmax pipelines never drain
-  // between items and the prologue (barrier init, TMEM allocation) is paid once per CTA.
-  const int n_qgroups = (p.Nq + NQT * BQ - 1) / (NQT * BQ);
-  const int total_items = p.B * p.H * n_qgroups;
-  auto item_nqt = [&](int item) {
-    const int q0 = (item % n_qgroups) * NQT * BQ;
-    return (NQT == 2 && q0 + BQ < p.Nq) ? 2 : 1;
-  };
+  const int n_qt = (NQT == 2 && q0 + BQ < p.Nq) ? 2 : 1;  // query tiles handled by this CTA
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&map_q);
@@ -95,7 +89,6 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
   if (warp_idx == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&s_free[i], 128);
       mbar_init(&p_full[i], 128);
@@ -103,9 +96,9 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
     }
     for (int i = 0; i < KS; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], NQT);  // one tcgen05.commit per query tile (two commits when an item has one tile)
+      mbar_init(&k_empty[i], n_qt);  // one tcgen05.commit per query tile that consumed the stage
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], NQT);
+      mbar_init(&v_empty[i], n_qt);
     }
     fence_barrier_init();
   }
@@ -123,34 +116,23 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
   if (warp_idx == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
-      uint32_t kv_g = 0;              // K / V tiles loaded so far (ring position)
-      uint32_t q_cnt[2] = {0, 0};     // items loaded per query-tile slot
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int qg = item % n_qgroups;
-        const int head = (item / n_qgroups) % p.H;
-        const int batch = item / (n_qgroups * p.H);
-        const int q0 = qg * NQT * BQ;
-        const int n_qt = item_nqt(item);
-        for (int qt = 0; qt < n_qt; ++qt) {
-          mbar_wait(&q_empty[qt], (q_cnt[qt] & 1) ^ 1);  // the previous item's last QK of this slot has retired
-          ++q_cnt[qt];
-          mbar_arrive_expect_tx(&q_full[qt], TILE_BYTES);
-          for (int a = 0; a < NA; ++a)
-            tma_load_3d(sQ + qt * TILE_BYTES + a * ATOM_BYTES, &map_q, &q_full[qt], head * HD + a * 64, q0 + qt * BQ,
-                        batch);
-        }
-        for (int j = 0; j < n_tiles; ++j, ++kv_g) {
-          const int s = kv_g % KS;
-          const uint32_t ph = (kv_g / KS) & 1;
-          mbar_wait(&k_empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
-          for (int a = 0; a < NA; ++a)
-            tma_load_3d(sK + s * TILE_BYTES + a * ATOM_BYTES, &map_k, &k_full[s], head * HD + a * 64, j * BKV, batch);
-          mbar_wait(&v_empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
-          for (int a = 0; a < NA; ++a)
-            tma_load_3d(sV + s * TILE_BYTES + a * ATOM_BYTES, &map_v, &v_full[s], head * HD + a * 64, j * BKV, batch);
-        }
+      for (int qt = 0; qt < n_qt; ++qt) {
+        mbar_arrive_expect_tx(&q_full[qt], TILE_BYTES);
+        for (int a = 0; a < NA; ++a)
+          tma_load_3d(sQ + qt * TILE_BYTES + a * ATOM_BYTES, &map_q, &q_full[qt], head * HD + a * 64, q0 + qt * BQ,
+                      batch);
+      }
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % KS;
+        const uint32_t ph = (j / KS) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
+        for (int a = 0; a < NA; ++a)
+          tma_load_3d(sK + s * TILE_BYTES + a * ATOM_BYTES, &map_k, &k_full[s], head * HD + a * 64, j * BKV, batch);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
+        for (int a = 0; a < NA; ++a)
+          tma_load_3d(sV + s * TILE_BYTES + a * ATOM_BYTES, &map_v, &v_full[s], head * HD + a * 64, j * BKV, batch);
       }
     }
   } else if (warp_idx == 1) {
@@ -158,197 +140,174 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc_qk = make_idesc_f16(128, BKV, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_f16(128, HD, 0, 1);  // B (= V) is MN-major
-      auto issue_qk = [&](int qt, uint32_t kv_idx) {
+      auto issue_qk = [&](int qt, int j) {
 #pragma unroll
         for (int a = 0; a < NA; ++a) {  // K dimension = head dim: one 64-wide swizzle atom at a time
           const uint64_t q_desc = make_sdesc_sw128(smem_u32(sQ + qt * TILE_BYTES + a * ATOM_BYTES), 1024, 0);
-          const uint64_t k_desc = make_sdesc_sw128(smem_u32(sK + (kv_idx % KS) * TILE_BYTES + a * ATOM_BYTES), 1024, 0);
+          const uint64_t k_desc = make_sdesc_sw128(smem_u32(sK + (j % KS) * TILE_BYTES + a * ATOM_BYTES), 1024, 0);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_f16(tmem_base + qt * BKV, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, (a | k) != 0 ? 1u : 0u);
         }
         umma_commit(&s_full[qt]);
       };
-      auto issue_pv = [&](int qt, uint32_t kv_idx, bool first) {
+      auto issue_pv = [&](int qt, int j) {
         // V tile: 128 kv rows x HD d as NA atoms of [128 rows x 64 d] (128 B per row, swizzled) = MN-major B operand:
         // 8-row K groups are 1024 B apart (SBO), 64-wide N atoms 16 KB apart (LBO); a K step of 16 rows advances 2048 B.
-        const uint64_t v_desc = make_sdesc_sw128(smem_u32(sV + (kv_idx % KS) * TILE_BYTES), 1024, ATOM_BYTES);
+        const uint64_t v_desc = make_sdesc_sw128(smem_u32(sV + (j % KS) * TILE_BYTES), 1024, ATOM_BYTES);
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
           const uint64_t p_desc =
               make_sdesc_sw128(smem_u32(sP + qt * A::P_BYTES + (k >> 2) * ATOM_BYTES), 1024, 0) + 2 * (k & 3);
-          umma_f16(tmem_base + O_COL + qt * HD, p_desc, v_desc + 128 * k, idesc_pv, (!first || k != 0) ? 1u : 0u);
+          umma_f16(tmem_base + O_COL + qt * HD, p_desc, v_desc + 128 * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
         }
         umma_commit(&pv_done[qt]);
       };
-      uint32_t kv_base = 0;           // ring position of this item's first K / V tile
-      uint32_t tq[2] = {0, 0};        // kv tiles processed so far per query-tile slot (phase of s_* / p_* / pv_done)
-      uint32_t q_cnt[2] = {0, 0};
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int n_qt = item_nqt(item);
-        int next_qk[2] = {0, 0}, next_pv[2] = {0, 0};
-        int remaining = n_qt * 2 * n_tiles;
-        long long t_start = clock64();
-        bool q_ready[2] = {false, false};
-        while (remaining > 0) {
-          bool progressed = false;
-          for (int qt = 0; qt < n_qt; ++qt) {
-            int j = next_pv[qt];
-            if (j < n_tiles && j < next_qk[qt] && mbar_try_wait(&p_full[qt], (tq[qt] + j) & 1) &&
-                mbar_try_wait(&v_full[(kv_base + j) % KS], ((kv_base + j) / KS) & 1)) {
-              tc_fence_after();
-              issue_pv(qt, kv_base + j, j == 0);
-              umma_commit(&v_empty[(kv_base + j) % KS]);
-              if (NQT == 2 && n_qt == 1) umma_commit(&v_empty[(kv_base + j) % KS]);
-              ++next_pv[qt];
-              --remaining;
-              progressed = true;
-            }
-            j = next_qk[qt];
-            if (j < n_tiles) {
-              if (!q_ready[qt]) q_ready[qt] = mbar_try_wait(&q_full[qt], q_cnt[qt] & 1);
-              const uint32_t g = tq[qt] + j;  // S_q must have been read out by the softmax warps (tile g-1)
-              if (q_ready[qt] && (g == 0 || mbar_try_wait(&s_free[qt], (g - 1) & 1)) &&
-                  mbar_try_wait(&k_full[(kv_base + j) % KS], ((kv_base + j) / KS) & 1)) {
-                tc_fence_after();
-                issue_qk(qt, kv_base + j);
-                umma_commit(&k_empty[(kv_base + j) % KS]);
-                if (NQT == 2 && n_qt == 1) umma_commit(&k_empty[(kv_base + j) % KS]);
-                if (j == n_tiles - 1) umma_commit(&q_empty[qt]);  // Q slot reusable once this QK retires
-                ++next_qk[qt];
-                --remaining;
-                progressed = true;
-              }
-            }
-          }
-          if (progressed) {
-            t_start = clock64();
-          } else if (clock64() - t_start > 4000000000LL) {
-            printf("cfgpp: attention MMA issuer stalled (block %d item %d)\n", blockIdx.x, item);
-            __trap();
-          }
-        }
+      for (int qt = 0; qt < n_qt; ++qt) mbar_wait(&q_full[qt], 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      for (int qt = 0; qt < n_qt; ++qt) {
+        issue_qk(qt, 0);
+        umma_commit(&k_empty[0]);
+      }
+      int next_qk[2] = {1, 1}, next_pv[2] = {0, 0};
+      int remaining = n_qt * (2 * n_tiles - 1);
+      long long t_start = clock64();
+      while (remaining > 0) {
+        bool progressed = false;
         for (int qt = 0; qt < n_qt; ++qt) {
-          tq[qt] += n_tiles;
-          ++q_cnt[qt];
+          int j = next_pv[qt];
+          if (j < n_tiles && mbar_try_wait(&p_full[qt], j & 1) && mbar_try_wait(&v_full[j % KS], (j / KS) & 1)) {
+            tc_fence_after();
+            issue_pv(qt, j);
+            umma_commit(&v_empty[j % KS]);
+            ++next_pv[qt];
+            --remaining;
+            progressed = true;
+          }
+          j = next_qk[qt];
+          if (j < n_tiles && mbar_try_wait(&s_free[qt], (j - 1) & 1) && mbar_try_wait(&k_full[j % KS], (j / KS) & 1)) {
+            tc_fence_after();
+            issue_qk(qt, j);
+            umma_commit(&k_empty[j % KS]);
+            ++next_qk[qt];
+            --remaining;
+            progressed = true;
+          }
         }
-        kv_base += n_tiles;
+        if (progressed) {
+          t_start = clock64();
+        } else if (clock64() - t_start > 4000000000LL) {
+          printf("cfgpp: attention MMA issuer stalled (block %d,%d,%d)\n", blockIdx.x, blockIdx.y, blockIdx.z);
+          __trap();
+        }
       }
     }
   } else if (warp_idx >= 4) {
     // ===================== softmax / output =====================
     const int qt = (warp_idx - 4) >> 2;
-    const int qw = warp_idx & 3;  // TMEM lane quarter of this warp
-    const int row = qw * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(qw * 32) << 16;
-    const uint32_t s_addr = tmem_base + qt * BKV + lane_off;
-    const uint32_t o_addr = tmem_base + O_COL + qt * HD + lane_off;
-    uint8_t* prow = sP + qt * A::P_BYTES + row * 128;
-    const float c = p.scale_log2e;
-    uint32_t tg = 0;  // kv tiles processed so far by this slot (barrier phases)
-    if (qt < NQT) {
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        if (qt >= item_nqt(item)) continue;
-        const int qg = item % n_qgroups;
-        const int head = (item / n_qgroups) % p.H;
-        const int batch = item / (n_qgroups * p.H);
-        const int q0 = qg * NQT * BQ;
-        float m_ref = -INFINITY, l_run = 0.f;
+    if (qt < n_qt) {
+      const int qw = warp_idx & 3;  // TMEM lane quarter of this warp
+      const int row = qw * 32 + lane;
+      const uint32_t lane_off = static_cast<uint32_t>(qw * 32) << 16;
+      const uint32_t s_addr = tmem_base + qt * BKV + lane_off;
+      const uint32_t o_addr = tmem_base + O_COL + qt * HD + lane_off;
+      uint8_t* prow = sP + qt * A::P_BYTES + row * 128;
+      const float c = p.scale_log2e;
+      float m_ref = -INFINITY, l_run = 0.f;
 
-        for (int j = 0; j < n_tiles; ++j, ++tg) {
-          const int valid = p.Nkv - j * BKV;  // columns >= valid are padding (last tile only)
-          mbar_wait(&s_full[qt], tg & 1);
-          tc_fence_after();
-          uint32_t s[128];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) tmem_ld_x32(s_addr + g * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[g * 32]));
-          tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive(&s_free[qt]);  // scores are in registers: the tensor pipe may already produce the next S_q
-          if (valid < BKV) {
-#pragma unroll
-            for (int i = 0; i < 128; ++i)
-              if (i >= valid) s[i] = 0xff800000u;  // -inf
-          }
-          float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
-#pragma unroll
-          for (int i = 2; i < 128; i += 2) {
-            mx0 = fmaxf(mx0, __uint_as_float(s[i]));
-            mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
-          }
-          const float mx = fmaxf(mx0, mx1);
-          // lazy running max: move the reference only when it would otherwise leave the comfortable range
-          float alpha = 1.0f;
-          bool need = false;
-          if (j == 0) {
-            m_ref = mx;
-          } else if ((mx - m_ref) * c > kRescaleThreshold) {
-            alpha = fast_exp2((m_ref - mx) * c);
-            m_ref = mx;
-            need = true;
-          }
-          if (j > 0) {
-            mbar_wait(&pv_done[qt], (tg - 1) & 1);  // previous PV retired: P buffer reusable, O_q rescalable
-            tc_fence_after();
-            if (__any_sync(0xffffffffu, need)) {
-#pragma unroll 1
-              for (int h = 0; h < HD / 16; ++h) {  // 16 columns at a time: the 128 scores stay live in registers
-                uint32_t o[16];
-                tmem_ld_x16(o_addr + h * 16, o);
-                tmem_ld_wait();
-#pragma unroll
-                for (int d = 0; d < 16; ++d) o[d] = __float_as_uint(__uint_as_float(o[d]) * alpha);
-                tmem_st_x16(o_addr + h * 16, o);
-              }
-              tmem_st_wait();
-              l_run *= alpha;
-            }
-          }
-          const float mc = m_ref * c;
-          float rs0 = 0.f, rs1 = 0.f;
-#pragma unroll
-          for (int g = 0; g < 16; ++g) {  // 16-byte chunks of the 256-byte P row (two 128-byte halves)
-            uint32_t pk[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float p0 = fast_exp2(__uint_as_float(s[g * 8 + 2 * e]) * c - mc);
-              const float p1 = fast_exp2(__uint_as_float(s[g * 8 + 2 * e + 1]) * c - mc);
-              rs0 += p0;
-              rs1 += p1;
-              pk[e] = pack_half2(p0, p1);
-            }
-            const int half_idx = g >> 3;        // which 64-column half
-            const int ch = (g & 7) ^ (row & 7);  // 128B swizzle
-            *reinterpret_cast<uint4*>(prow + half_idx * ATOM_BYTES + ch * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          }
-          l_run += rs0 + rs1;
-          tc_fence_before();
-          fence_proxy_async_smem();
-          mbar_arrive(&p_full[qt]);
-        }
-        mbar_wait(&pv_done[qt], (tg - 1) & 1);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int valid = p.Nkv - j * BKV;  // columns >= valid are padding (last tile only)
+        mbar_wait(&s_full[qt], j & 1);
         tc_fence_after();
-        const float inv_l = 1.0f / l_run;
-        const int qrow = q0 + qt * BQ + row;
-        __half* dst = p.out + (static_cast<size_t>(batch) * p.Nq + qrow) * p.ldo + head * HD;
-#pragma unroll 1
-        for (int h = 0; h < HD / 32; ++h) {
-          uint32_t o[32];
-          tmem_ld_x32(o_addr + h * 32, o);
-          tmem_ld_wait();
-          if (qrow < p.Nq) {
+        uint32_t s[128];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 w;
-              w.x = pack_half2(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
-              w.y = pack_half2(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
-              w.z = pack_half2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
-              w.w = pack_half2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
-              reinterpret_cast<uint4*>(dst + h * 32)[i] = w;
+        for (int g = 0; g < 4; ++g) tmem_ld_x32(s_addr + g * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[g * 32]));
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_free[qt]);  // scores are in registers: the tensor pipe may already produce S_q(j+1)
+        if (valid < BKV) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (i >= valid) s[i] = 0xff800000u;  // -inf
+        }
+        float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
+#pragma unroll
+        for (int i = 2; i < 128; i += 2) {
+          mx0 = fmaxf(mx0, __uint_as_float(s[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+        }
+        const float mx = fmaxf(mx0, mx1);
+        // lazy running max: move the reference only when it would otherwise overflow the comfortable range
+        float alpha = 1.0f;
+        bool need = false;
+        if (j == 0) {
+          m_ref = mx;
+        } else if ((mx - m_ref) * c > kRescaleThreshold) {
+          alpha = fast_exp2((m_ref - mx) * c);
+          m_ref = mx;
+          need = true;
+        }
+        if (j > 0) {
+          mbar_wait(&pv_done[qt], (j - 1) & 1);  // PV_q(j-1) retired: P buffer reusable, O_q rescalable
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, need)) {
+#pragma unroll 1
+            for (int h = 0; h < HD / 16; ++h) {  // 16 columns at a time: the 128 scores stay live in registers
+              uint32_t o[16];
+              tmem_ld_x16(o_addr + h * 16, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int d = 0; d < 16; ++d) o[d] = __float_as_uint(__uint_as_float(o[d]) * alpha);
+              tmem_st_x16(o_addr + h * 16, o);
             }
+            tmem_st_wait();
+            l_run *= alpha;
           }
         }
-        tc_fence_before();  // O_q has been read out before this slot signals p_full for the next item
+        const float mc = m_ref * c;
+        float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {  // 16-byte chunks of the 256-byte P row (two 128-byte halves)
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float p0 = fast_exp2(__uint_as_float(s[g * 8 + 2 * e]) * c - mc);
+            const float p1 = fast_exp2(__uint_as_float(s[g * 8 + 2 * e + 1]) * c - mc);
+            rs0 += p0;
+            rs1 += p1;
+            pk[e] = pack_half2(p0, p1);
+          }
+          const int half_idx = g >> 3;        // which 64-column half
+          const int ch = (g & 7) ^ (row & 7);  // 128B swizzle
+          *reinterpret_cast<uint4*>(prow + half_idx * ATOM_BYTES + ch * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        l_run += rs0 + rs1;
+        tc_fence_before();
+        fence_proxy_async_smem();
+        mbar_arrive(&p_full[qt]);
+      }
+      mbar_wait(&pv_done[qt], (n_tiles - 1) & 1);
+      tc_fence_after();
+      const float inv_l = 1.0f / l_run;
+      const int qrow = q0 + qt * BQ + row;
+      __half* dst = p.out + (static_cast<size_t>(batch) * p.Nq + qrow) * p.ldo + head * HD;
+#pragma unroll 1
+      for (int h = 0; h < HD / 32; ++h) {
+        uint32_t o[32];
+        tmem_ld_x32(o_addr + h * 32, o);
+        tmem_ld_wait();
+        if (qrow < p.Nq) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 w;
+            w.x = pack_half2(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
+            w.y = pack_half2(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
+            w.z = pack_half2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
+            w.w = pack_half2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
+            reinterpret_cast<uint4*>(dst + h * 32)[i] = w;
+          }
+        }
       }
     }
   }
@@ -376,10 +335,9 @@ void configure_one() {
 
 template <int HD, int NQT, int KS>
 void launch(const AttnOp& op, cudaStream_t stream) {
-  const int items = ((op.p.Nq + NQT * BQ - 1) / (NQT * BQ)) * op.p.H * op.p.B;
-  const int grid = items < num_sms() ? items : num_sms();
-  launch_pdl(attn_kernel<HD, NQT, KS>, dim3(grid), dim3(kThreads), ACfg<HD, NQT, KS>::SMEM_BYTES, stream, op.p,
-             op.map_q, op.map_k, op.map_v);
+  dim3 grid((op.p.Nq + NQT * BQ - 1) / (NQT * BQ), op.p.H, op.p.B);
+  launch_pdl(attn_kernel<HD, NQT, KS>, grid, dim3(kThreads), ACfg<HD, NQT, KS>::SMEM_BYTES, stream, op.p, op.map_q,
+             op.map_k, op.map_v);
 }
 
 }  // namespace
