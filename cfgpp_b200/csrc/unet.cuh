@@ -94,6 +94,8 @@ class Unet {
   void add_attn(const std::string& name, const AttnOp& op);
   void add_step(const std::string& name, std::function<void(cudaStream_t)> fn, int launches = 1);
   void run_plan(const std::vector<PlanStep>& plan, cudaStream_t stream);
+  void run_body(cudaStream_t stream, bool concurrent);
+  static bool split_disabled();
   void build_final(int mode_with_dtype, bool expose_eps);
   void ensure_graph(cudaStream_t stream);
 
@@ -117,7 +119,14 @@ class Unet {
   int B_ = 0, NB_ = 0, H_ = 0, W_ = 0;
   std::vector<PlanStep>* cur_plan_ = nullptr;
   std::vector<PlanStep> prologue_plan_;  // timestep embedding -> temb for all resnets
-  std::vector<PlanStep> body_plan_;      // conv_in .. last up block + conv_norm_out
+  std::vector<PlanStep> branch_plan_[2];  // conv_in output .. last up block, one plan per CFG half (uncond / cond)
+  std::vector<PlanStep> tail_plan_;       // conv_norm_out + SiLU over the whole batch
+  int n_branches_ = 1;
+  // branch currently being built (rows [brow0_, brow0_ + bnb_) of the UNet batch)
+  int bnb_ = 0, brow0_ = 0;
+  std::string btag_;
+  float* bgn_partial_ = nullptr;
+  __half* out_override_ = nullptr;
   std::vector<PlanStep> prompt_plan_;    // cross-attention K/V projections + add-embedding
   double forward_flops_ = 0.0;
   int launches_per_step_ = 0;
@@ -158,6 +167,8 @@ class Unet {
   cudaGraphExec_t graph_exec_ = nullptr;
   bool graph_valid_ = false;
   cudaStream_t capture_stream_ = nullptr;
+  cudaStream_t capture_stream2_ = nullptr;
+  cudaEvent_t fork_ev_ = nullptr, join_ev_ = nullptr;
 };
 
 }  // namespace cfgpp
