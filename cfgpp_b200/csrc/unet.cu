@@ -821,7 +821,7 @@ void Unet::unet_forward(const void* z, int z_dtype, float t, float in_scale, __h
   run_plan(prologue_plan_, stream);
   run_conv_in(z, z_dtype == CFGPP_F16 ? 1 : 0, &cur_state_->in_scale, conv_in_w_, conv_in_b_, conv_in_out_, B_, H_, W_,
               d_.block_out_channels[0], 2, stream);
-  run_body(stream, false);
+  run_body(stream, true);  // the two CFG halves fork onto a side stream and join before the tail
   run_conv_out_step(final_norm_.p, conv_out_w_, conv_out_b_, B_, H_, W_, final_norm_.C, STEP_NONE, nullptr, nullptr,
                     nullptr, nullptr, eps_uc, eps_c, stream);
 }
