@@ -14,6 +14,8 @@ int num_sms() {
     int dev = 0;
     CFGPP_CHECK_CUDA(cudaGetDevice(&dev));
     CFGPP_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    const char* cap = getenv("CFGPP_SM_CAP");  // experiment knob: persistent grids use at most this many SMs
+    if (cap && atoi(cap) > 0 && atoi(cap) < n) n = atoi(cap);
   }
   return n;
 }
