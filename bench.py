@@ -35,6 +35,11 @@ LAMBDA = 0.6
 BATCH = 2
 LATENT = 128
 METRIC = "images/sec (device-timed) SDXL 1024x1024 NFE=50 ddim_cfg++"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, mean over the 12 consecutive
+# gemm_kernel launches of a 1280-channel transformer block in one `ncu --set full` capture (cold L2: an upper bound;
+# it equals the algorithmic A + W + residual bytes, i.e. no re-reads) — profiles/r01_v2_ncu_full.md
+NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 32.83e6
+NCU_TRAFFIC_SOURCE = "ncu --set full, gpurun_out/prof_gemm.ncu-rep (round 1 v2), summarised in profiles/r01_v2_ncu_full.md"
 
 
 def measured_peaks():
@@ -307,9 +312,10 @@ def run_ours(args):
     gemm_n = by_kind[0][2] + by_kind[1][2]
     tot_ms = sum(v[1] for v in by_kind.values())
     achieved = gemm_fl / (gemm_ms / 1e3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "gemm_kernel<BN,GEGLU> (tcgen05 GEMM + implicit-GEMM conv3x3)",
+    roofline = {"bound": "tensor", "kernel": "gemm_kernel<BN,GEGLU,CL> (tcgen05 GEMM + implicit-GEMM conv3x3)",
                 "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                "traffic": None, "peak_source": peaks["source"] + " (bf16 sustained)",
+                "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH, "traffic_source": NCU_TRAFFIC_SOURCE,
+                "peak_source": peaks["source"] + " (bf16 sustained)",
                 "flops_per_launch": gemm_fl / max(gemm_n, 1), "launches_per_forward": gemm_n,
                 "avg_launch_us": 1e3 * gemm_ms / max(gemm_n, 1), "share_of_step": gemm_ms / tot_ms,
                 "by_kind_ms": {"linear_gemm": by_kind[0][1], "conv3x3": by_kind[1][1], "attention": by_kind[2][1],
