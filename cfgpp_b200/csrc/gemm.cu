@@ -32,10 +32,11 @@ struct Cfg {
   static constexpr int EPI_SUB_BYTES = BM * 64;
   static constexpr int EPI_BYTES = EPI_SUB * EPI_SUB_BYTES;
   static constexpr int STAGES =
-      CL == 2 ? (GEGLU ? 6 : (BN == 256 ? 5 : 6)) : (GEGLU ? 4 : (BN == 256 ? 3 : (BN == 160 ? 5 : 6)));
+      CL == 2 ? (GEGLU ? 5 : (BN == 256 ? 4 : 6)) : (GEGLU ? 3 : (BN == 256 ? 3 : 5));
   static constexpr int TMEM_COLS = (BN <= 64) ? 128 : (BN <= 128 ? 256 : 512);
   static constexpr int ACC_STRIDE = TMEM_COLS / 2;
-  static constexpr int VEC_BYTES = 2 * 256 * 2;  // per-tile bias and time-embedding row staged for the epilogue
+  // per-tile vectors staged for the epilogue: bias + time-embedding row (fp16), LayerNorm-fold s_n / t_n (fp32)
+  static constexpr int VEC_BYTES = 2 * 256 * 2 + 2 * 256 * 4;
   static constexpr int SMEM_BYTES =
       STAGES * STAGE_BYTES + EPI_BYTES + VEC_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of an SM");
@@ -62,6 +63,8 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
   uint8_t* epi_smem = smem + C::STAGES * C::STAGE_BYTES;
   __half* s_bias = reinterpret_cast<__half*>(epi_smem + C::EPI_BYTES);  // [256]
   __half* s_temb = s_bias + 256;                                         // [256]
+  float* s_lns = reinterpret_cast<float*>(s_temb + 256);                 // [256]
+  float* s_lnt = s_lns + 256;                                            // [256]
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + C::EPI_BYTES + C::VEC_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::STAGES;
@@ -281,8 +284,27 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
           const bool ok = n < p.N;
           if (p.bias) s_bias[c] = ok ? p.bias[n] : __float2half(0.f);
           if (temb_staged) s_temb[c] = ok ? add_row[n] : __float2half(0.f);
+          if (p.stats_in) {
+            s_lns[c] = ok ? p.ln_s[n] : 0.f;
+            s_lnt[c] = ok ? p.ln_t[n] : 0.f;
+          }
         }
       }
+      // LayerNorm fold: this row's mean / rstd from the producer's per-N-block partial sums (fixed order)
+      float ln_rstd = 1.f, ln_rm = 0.f;
+      if (p.stats_in && m < p.M) {
+        float sx = 0.f, sxx = 0.f;
+        for (int i = 0; i < p.ln_parts; ++i) {
+          const float2 v = *reinterpret_cast<const float2*>(p.stats_in + (static_cast<size_t>(i) * p.M + m) * 2);
+          sx += v.x;
+          sxx += v.y;
+        }
+        const float mean = sx * p.ln_inv_c;
+        const float var = fmaxf(sxx * p.ln_inv_c - mean * mean, 0.f);
+        ln_rstd = rsqrtf(var + p.ln_eps);
+        ln_rm = ln_rstd * mean;
+      }
+      float ps = 0.f, pss = 0.f;  // producer side: partial row statistics of this tile's fp16 outputs
       mbar_wait(&tmem_full_bar[as], aph);
       if (leader) { if (it == 0) TL(7); TL(9); if (tl) tl[12] = it + 1; }
       tc_fence_after();
@@ -308,7 +330,10 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
             for (int e = 0; e < 4; ++e) {
               const int jj = c * 4 + e;  // half2 index within the 32-column chunk
               float x0 = __uint_as_float(v[2 * jj]), x1 = __uint_as_float(v[2 * jj + 1]);
-              if (p.bias) {
+              if (p.stats_in) {
+                x0 = x0 * ln_rstd - ln_rm * s_lns[j * 32 + 2 * jj] + s_lnt[j * 32 + 2 * jj];
+                x1 = x1 * ln_rstd - ln_rm * s_lns[j * 32 + 2 * jj + 1] + s_lnt[j * 32 + 2 * jj + 1];
+              } else if (p.bias) {
                 const __half2 b = *reinterpret_cast<const __half2*>(s_bias + j * 32 + 2 * jj);
                 x0 += __low2float(b);
                 x1 += __high2float(b);
@@ -328,11 +353,18 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
                 }
                 t = __floats2half2_rn(__low2float(t) + a0, __high2float(t) + a1);
               }
+              if (p.stats_out) {
+                const float f0 = __low2float(t), f1 = __high2float(t);
+                ps += f0 + f1;
+                pss += f0 * f0 + f1 * f1;
+              }
               o[jj] = *reinterpret_cast<uint32_t*>(&t);
             }
             *reinterpret_cast<uint4*>(srow + ((c ^ sw) << 4)) = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
           }
         }
+        if (p.stats_out && m < p.M)
+          *reinterpret_cast<float2*>(p.stats_out + (static_cast<size_t>(n_blk) * p.M + m) * 2) = make_float2(ps, pss);
       } else {
         // value columns [0,128), gate columns [128,256) of this tile -> 128 output columns
 #pragma unroll 1
@@ -347,7 +379,13 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
           for (int jj = 0; jj < 16; ++jj) {
             float a0 = __uint_as_float(va[2 * jj]), a1 = __uint_as_float(va[2 * jj + 1]);
             float g0 = __uint_as_float(vg[2 * jj]), g1 = __uint_as_float(vg[2 * jj + 1]);
-            if (p.bias) {
+            if (p.stats_in) {
+              const int ia = j * 32 + 2 * jj, ig = BN / 2 + j * 32 + 2 * jj;
+              a0 = a0 * ln_rstd - ln_rm * s_lns[ia] + s_lnt[ia];
+              a1 = a1 * ln_rstd - ln_rm * s_lns[ia + 1] + s_lnt[ia + 1];
+              g0 = g0 * ln_rstd - ln_rm * s_lns[ig] + s_lnt[ig];
+              g1 = g1 * ln_rstd - ln_rm * s_lns[ig + 1] + s_lnt[ig + 1];
+            } else if (p.bias) {
               const __half2 ba = *reinterpret_cast<const __half2*>(s_bias + j * 32 + 2 * jj);
               const __half2 bg = *reinterpret_cast<const __half2*>(s_bias + BN / 2 + j * 32 + 2 * jj);
               a0 += __low2float(ba);

@@ -35,6 +35,17 @@ struct GemmParams {
   int ldc;
   int geglu;
   unsigned long long* timeline;  // debug: per-CTA timestamps (16 slots each), nullptr in production
+  // ---- LayerNorm folded into the GEMM (no separate LN pass over the activations) -------------------------------
+  // LN(h) W^T = rstd_m * (h (gamma (.) W)^T)_mn - rstd_m * mean_m * s_n + t_n ,  s_n = sum_k (gamma (.) W)_nk ,
+  // t_n = sum_k beta_k W_nk (+ bias_n). The GEMM that PRODUCES h writes per-row partial (sum, sum of squares) of its
+  // fp16 output, one slot per N block (deterministic, no atomics); the GEMM that CONSUMES LN(h) runs on h directly
+  // with the folded weight and applies the row / column corrections in its epilogue.
+  float* stats_out;        // producer: [num_n_blocks][M] float2, or null
+  const float* stats_in;   // consumer: [ln_parts][M] float2, or null
+  int ln_parts;
+  float ln_inv_c, ln_eps;
+  const float* ln_s;       // [N] fp32
+  const float* ln_t;       // [N] fp32
 };
 
 struct GemmOp {

@@ -74,6 +74,33 @@ __global__ void pack_heads_cols_kernel(const __half* __restrict__ in, __half* __
   }
 }
 
+// LayerNorm fold (see GemmParams): one warp per (packed) weight row n
+__global__ void fold_ln_kernel(const __half* __restrict__ w, const __half* __restrict__ gamma,
+                               const __half* __restrict__ beta, const __half* __restrict__ bias,
+                               __half* __restrict__ wf, float* __restrict__ s_out, float* __restrict__ t_out, int N,
+                               int K) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float s = 0.f, t = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float wv = __half2float(w[static_cast<size_t>(n) * K + k]);
+    const __half wg = __float2half_rn(wv * __half2float(gamma[k]));
+    wf[static_cast<size_t>(n) * K + k] = wg;
+    s += __half2float(wg);
+    t += __half2float(beta[k]) * wv;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  if (lane == 0) {
+    s_out[n] = s;
+    t_out[n] = t + (bias ? __half2float(bias[n]) : 0.f);
+  }
+}
+
 int grid_for(size_t n) { return static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 8)); }
 
 }  // namespace
@@ -236,6 +263,31 @@ __half* Unet::packed_heads_cols(const std::string& key, int heads, int hd, int h
   return out;
 }
 
+Unet::FoldedLN Unet::folded_ln(const std::string& cache_key, const __half* w_packed, int N, int K,
+                               const std::string& norm_prefix, const __half* bias_packed) {
+  auto it = fold_cache_.find(cache_key);
+  if (it != fold_cache_.end()) return it->second;
+  FoldedLN f;
+  f.w = alloc_weight(static_cast<size_t>(N) * K);
+  f.s = reinterpret_cast<float*>(alloc_weight(static_cast<size_t>(N) * 2));
+  f.t = reinterpret_cast<float*>(alloc_weight(static_cast<size_t>(N) * 2));
+  const int warps = 8;
+  fold_ln_kernel<<<(N + warps - 1) / warps, warps * 32>>>(w_packed, plain(norm_prefix + ".weight"),
+                                                           plain(norm_prefix + ".bias"), bias_packed, f.w, f.s, f.t, N, K);
+  CFGPP_CHECK_CUDA(cudaGetLastError());
+  fold_cache_[cache_key] = f;
+  return f;
+}
+
+bool Unet::lnfold_disabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CFGPP_NO_LNFOLD");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 void Unet::finalize_weights(cudaStream_t stream) {
   CFGPP_CHECK_CUDA(cudaStreamSynchronize(stream));
   // structural validation: every key the plan will touch must exist (dry walk at a nominal size)
@@ -377,6 +429,9 @@ Unet::Act Unet::build_transformer(const std::string& prefix, Act x, int H, int W
   Scratch* s_attn = scratch(btag_ + "attn", M * Cp);
   Scratch* s_q = scratch(btag_ + "q", M * Cp);
   Scratch* s_ff = scratch(btag_ + "ff", M * 4 * C);
+  Scratch* s_stats[3];
+  for (int i = 0; i < 3; ++i)  // [16 N blocks][M] float2 partial row statistics (LayerNorm fold)
+    s_stats[i] = scratch(btag_ + "lnstats" + std::to_string(i), static_cast<size_t>(16) * M * 2 * 2);
   __half* out = g_dry ? nullptr : alloc_act(M * C);
   const int Mkv = bnb_ * n_ctx_;
   if (g_dry) {
@@ -399,6 +454,39 @@ Unet::Act Unet::build_transformer(const std::string& prefix, Act x, int H, int W
   const int NB = bnb_;
   float* partial = bgn_partial_;
   __half *normp = s_norm->p, *tok = s_tok->p, *qkv = s_qkv->p, *attn = s_attn->p, *qb = s_q->p, *ff = s_ff->p;
+  // LayerNorm fold: the GEMMs that write the residual stream `tok` also emit per-row partial statistics, and the
+  // GEMMs that read LN(tok) run on `tok` with gamma folded into the weight (no LayerNorm launches at all)
+  const bool fold = !lnfold_disabled();
+  float* stats[3] = {nullptr, nullptr, nullptr};
+  int parts[3] = {0, 0, 0};
+  if (fold)
+    for (int i = 0; i < 3; ++i) stats[i] = reinterpret_cast<float*>(s_stats[i]->p);
+  // a producer's N blocks must tile C exactly so that every column contributes to the row statistics
+  auto producer = [&](const std::function<GemmOp(int)>& make, int slot) {
+    GemmOp op = make(0);
+    if (fold) {
+      if (C % op.bn != 0) {
+        for (int bn : {160, 128, 64})
+          if (C % bn == 0) {
+            op = make(bn);
+            break;
+          }
+      }
+      CFGPP_REQUIRE(C % op.bn == 0 && op.p.num_n_blocks <= 16, "LayerNorm fold: no tile width divides C");
+      op.p.stats_out = stats[slot];
+      parts[slot] = op.p.num_n_blocks;
+    }
+    return op;
+  };
+  auto consumer = [&](GemmOp op, const FoldedLN& f, int slot) {
+    op.p.stats_in = stats[slot];
+    op.p.ln_parts = parts[slot];
+    op.p.ln_inv_c = 1.0f / static_cast<float>(C);
+    op.p.ln_eps = 1e-5f;
+    op.p.ln_s = f.s;
+    op.p.ln_t = f.t;
+    return op;
+  };
   {
     const __half *g = plain(prefix + ".norm.weight"), *b = plain(prefix + ".norm.bias");
     const __half* xp = x.p;
@@ -406,8 +494,10 @@ Unet::Act Unet::build_transformer(const std::string& prefix, Act x, int H, int W
       run_groupnorm(xp, C, nullptr, 0, NB, HW, g, b, 1e-6f, false, partial, normp, st);
     }, 2);
   }
-  add_gemm(prefix + ".proj_in", make_linear_op(normp, C, nullptr, 0, 0, plain(prefix + ".proj_in.weight"), Mi, C, C,
-                                               plain(prefix + ".proj_in.bias"), nullptr, 0, 1, tok, C, false));
+  add_gemm(prefix + ".proj_in", producer([&](int bn) {
+             return make_linear_op(normp, C, nullptr, 0, 0, plain(prefix + ".proj_in.weight"), Mi, C, C,
+                                   plain(prefix + ".proj_in.bias"), nullptr, 0, 1, tok, C, false, bn);
+           }, 0));
   for (int k = 0; k < layers; ++k) {
     const std::string b = prefix + ".transformer_blocks." + std::to_string(k);
     auto add_ln = [&](const std::string& n) {
@@ -415,46 +505,75 @@ Unet::Act Unet::build_transformer(const std::string& prefix, Act x, int H, int W
       add_step(b + n, [=](cudaStream_t st) { run_layernorm(tok, Mi, C, g, be, 1e-5f, normp, st); });
     };
     // --- self-attention ---
-    add_ln(".norm1");
     __half* wqkv = packed_heads_rows({b + ".attn1.to_q.weight", b + ".attn1.to_k.weight", b + ".attn1.to_v.weight"},
                                      heads, hd, hdp);
-    add_gemm(b + ".attn1.to_qkv",
-             make_linear_op(normp, C, nullptr, 0, 0, wqkv, Mi, 3 * Cp, C, nullptr, nullptr, 0, 1, qkv, 3 * Cp, false),
-             2.0 * Mi * 3.0 * C * C);
+    if (fold) {
+      const FoldedLN f = folded_ln(b + ".attn1.qkv", wqkv, 3 * Cp, C, b + ".norm1", nullptr);
+      add_gemm(b + ".attn1.to_qkv(+norm1)",
+               consumer(make_linear_op(tok, C, nullptr, 0, 0, f.w, Mi, 3 * Cp, C, nullptr, nullptr, 0, 1, qkv, 3 * Cp, false),
+                        f, 0),
+               2.0 * Mi * 3.0 * C * C);
+    } else {
+      add_ln(".norm1");
+      add_gemm(b + ".attn1.to_qkv",
+               make_linear_op(normp, C, nullptr, 0, 0, wqkv, Mi, 3 * Cp, C, nullptr, nullptr, 0, 1, qkv, 3 * Cp, false),
+               2.0 * Mi * 3.0 * C * C);
+    }
     add_attn(b + ".attn1.sdpa",
              make_attn_op(qkv, 3 * Cp, qkv + Cp, 3 * Cp, qkv + 2 * Cp, 3 * Cp, attn, Cp, bnb_, heads, HW, HW, hd));
-    add_gemm(b + ".attn1.to_out",
-             make_linear_op(attn, Cp, nullptr, 0, 0, packed_heads_cols(b + ".attn1.to_out.0.weight", heads, hd, hdp), Mi,
-                            C, Cp, plain(b + ".attn1.to_out.0.bias"), tok, C, 1, tok, C, false),
+    add_gemm(b + ".attn1.to_out", producer([&](int bn) {
+               return make_linear_op(attn, Cp, nullptr, 0, 0,
+                                     packed_heads_cols(b + ".attn1.to_out.0.weight", heads, hd, hdp), Mi, C, Cp,
+                                     plain(b + ".attn1.to_out.0.bias"), tok, C, 1, tok, C, false, bn);
+             }, 1),
              2.0 * Mi * static_cast<double>(C) * C);
     // --- cross-attention (K/V projected once per prompt by the prompt plan) ---
-    add_ln(".norm2");
-    add_gemm(b + ".attn2.to_q",
-             make_linear_op(normp, C, nullptr, 0, 0, packed_heads_rows({b + ".attn2.to_q.weight"}, heads, hd, hdp), Mi,
-                            Cp, C, nullptr, nullptr, 0, 1, qb, Cp, false),
-             2.0 * Mi * static_cast<double>(C) * C);
+    __half* wq2 = packed_heads_rows({b + ".attn2.to_q.weight"}, heads, hd, hdp);
+    if (fold) {
+      const FoldedLN f = folded_ln(b + ".attn2.q", wq2, Cp, C, b + ".norm2", nullptr);
+      add_gemm(b + ".attn2.to_q(+norm2)",
+               consumer(make_linear_op(tok, C, nullptr, 0, 0, f.w, Mi, Cp, C, nullptr, nullptr, 0, 1, qb, Cp, false), f, 1),
+               2.0 * Mi * static_cast<double>(C) * C);
+    } else {
+      add_ln(".norm2");
+      add_gemm(b + ".attn2.to_q",
+               make_linear_op(normp, C, nullptr, 0, 0, wq2, Mi, Cp, C, nullptr, nullptr, 0, 1, qb, Cp, false),
+               2.0 * Mi * static_cast<double>(C) * C);
+    }
     __half* kv = alloc_act(static_cast<size_t>(Mkv) * 2 * Cp);
     {
       __half* wkv = packed_heads_rows({b + ".attn2.to_k.weight", b + ".attn2.to_v.weight"}, heads, hd, hdp);
       std::vector<PlanStep>* save = cur_plan_;
       cur_plan_ = &prompt_plan_;
       add_gemm(b + ".attn2.to_kv",
-               make_linear_op(ctx_copy_ + static_cast<size_t>(brow0_) * n_ctx_ * D, D, nullptr, 0, 0, wkv, Mkv, 2 * Cp, D, nullptr, nullptr, 0, 1, kv, 2 * Cp, false),
+               make_linear_op(ctx_copy_ + static_cast<size_t>(brow0_) * n_ctx_ * D, D, nullptr, 0, 0, wkv, Mkv, 2 * Cp, D,
+                              nullptr, nullptr, 0, 1, kv, 2 * Cp, false),
                2.0 * Mkv * 2.0 * C * D);
       cur_plan_ = save;
     }
     add_attn(b + ".attn2.sdpa", make_attn_op(qb, Cp, kv, 2 * Cp, kv + Cp, 2 * Cp, attn, Cp, bnb_, heads, HW, n_ctx_, hd));
-    add_gemm(b + ".attn2.to_out",
-             make_linear_op(attn, Cp, nullptr, 0, 0, packed_heads_cols(b + ".attn2.to_out.0.weight", heads, hd, hdp), Mi,
-                            C, Cp, plain(b + ".attn2.to_out.0.bias"), tok, C, 1, tok, C, false),
+    add_gemm(b + ".attn2.to_out", producer([&](int bn) {
+               return make_linear_op(attn, Cp, nullptr, 0, 0,
+                                     packed_heads_cols(b + ".attn2.to_out.0.weight", heads, hd, hdp), Mi, C, Cp,
+                                     plain(b + ".attn2.to_out.0.bias"), tok, C, 1, tok, C, false, bn);
+             }, 2),
              2.0 * Mi * static_cast<double>(C) * C);
     // --- GEGLU feed-forward ---
-    add_ln(".norm3");
-    add_gemm(b + ".ff.geglu",
-             make_linear_op(normp, C, nullptr, 0, 0, packed_geglu(b + ".ff.net.0.proj.weight", false), Mi, 8 * C, C,
-                            packed_geglu(b + ".ff.net.0.proj.bias", true), nullptr, 0, 1, ff, 4 * C, true));
-    add_gemm(b + ".ff.out", make_linear_op(ff, 4 * C, nullptr, 0, 0, plain(b + ".ff.net.2.weight"), Mi, C, 4 * C,
-                                           plain(b + ".ff.net.2.bias"), tok, C, 1, tok, C, false));
+    __half* wg = packed_geglu(b + ".ff.net.0.proj.weight", false);
+    __half* bg = packed_geglu(b + ".ff.net.0.proj.bias", true);
+    if (fold) {
+      const FoldedLN f = folded_ln(b + ".ff.geglu", wg, 8 * C, C, b + ".norm3", bg);
+      add_gemm(b + ".ff.geglu(+norm3)",
+               consumer(make_linear_op(tok, C, nullptr, 0, 0, f.w, Mi, 8 * C, C, nullptr, nullptr, 0, 1, ff, 4 * C, true), f, 2));
+    } else {
+      add_ln(".norm3");
+      add_gemm(b + ".ff.geglu",
+               make_linear_op(normp, C, nullptr, 0, 0, wg, Mi, 8 * C, C, bg, nullptr, 0, 1, ff, 4 * C, true));
+    }
+    add_gemm(b + ".ff.out", producer([&](int bn) {
+               return make_linear_op(ff, 4 * C, nullptr, 0, 0, plain(b + ".ff.net.2.weight"), Mi, C, 4 * C,
+                                     plain(b + ".ff.net.2.bias"), tok, C, 1, tok, C, false, bn);
+             }, 0));
   }
   add_gemm(prefix + ".proj_out", make_linear_op(tok, C, nullptr, 0, 0, plain(prefix + ".proj_out.weight"), Mi, C, C,
                                                 plain(prefix + ".proj_out.bias"), x.p, C, 1, out, C, false));

@@ -72,6 +72,15 @@ class Unet {
   __half* packed_geglu(const std::string& key, bool is_bias);
   __half* packed_heads_rows(const std::vector<std::string>& keys, int heads, int hd, int hdp);
   __half* packed_heads_cols(const std::string& key, int heads, int hd, int hdp);
+  struct FoldedLN {
+    __half* w;
+    float* s;
+    float* t;
+  };
+  FoldedLN folded_ln(const std::string& cache_key, const __half* w_packed, int N, int K, const std::string& norm_prefix,
+                     const __half* bias_packed);
+  std::map<std::string, FoldedLN> fold_cache_;
+  static bool lnfold_disabled();
   __half* plain(const std::string& key);
 
   // ---- workspace ----
