@@ -40,6 +40,7 @@ CFGPP_DEVICE void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
 CFGPP_DEVICE void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Non-blocking probe (used by polling state machines): returns after the default, short, hardware time-out.
 CFGPP_DEVICE uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -53,12 +54,27 @@ CFGPP_DEVICE uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok;
 }
+// Probe with a suspend-time hint: the thread may sleep in hardware for up to ~1 ms waiting for the phase, instead
+// of spinning through the issue stage (128 epilogue threads per SM wait for a whole main loop on tmem_full).
+CFGPP_DEVICE uint32_t mbar_try_wait_sleep(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(1000000)
+      : "memory");
+  return ok;
+}
 // Wait for the phase with the given parity to complete. A wait that lasts > ~2 s of SM clocks can only be
 // a pipeline bug; trap (surfaces as a launch failure) instead of hanging the GPU.
 CFGPP_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_sleep(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {
       printf("cfgpp: mbarrier wait timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x,
              smem_u32(bar), parity);

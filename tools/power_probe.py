@@ -74,6 +74,11 @@ loop("gemm 8192^3", mk(8192, 8192, 8192), flops=2.0 * 8192 ** 3)
 loop("gemm geglu 4096x10240x1280", mk(4096, 10240, 1280, geglu=True), flops=2.0 * 4096 * 10240 * 1280)
 loop("gemm ff.out 4096x1280x5120 +res", mk(4096, 1280, 5120, True), flops=2.0 * 4096 * 1280 * 5120)
 loop("gemm to_out 4096x1280x1280 +res", mk(4096, 1280, 1280, True), flops=2.0 * 4096 * 1280 * 1280)
+for (M, N, K) in [(4096, 10240, 1280), (4096, 1280, 5120), (4096, 3840, 1280), (4096, 1280, 1280)]:
+    am = torch.randn(M, K, generator=g).half().to(dev)
+    wm = (torch.randn(N, K, generator=g) * K ** -0.5).half().to(dev)
+    loop(f"torch.matmul {M}x{N}x{K} (cuBLAS)", lambda: torch.matmul(am, wm.t()), flops=2.0 * M * N * K)
+    loop(f"ours plain   {M}x{N}x{K}", lambda: nv.op_linear(am, wm), flops=2.0 * M * N * K)
 a8 = torch.randn(8192, 8192, generator=g).half().to(dev)
 loop("torch.matmul 8192^3 (cuBLAS)", lambda: torch.matmul(a8, a8), flops=2.0 * 8192 ** 3)
 qkv = (torch.randn(4, 1024, 3 * 1280, generator=g) * 1.2).half().to(dev)
