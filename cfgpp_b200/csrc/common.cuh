@@ -211,6 +211,22 @@ CFGPP_DEVICE void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // whole warp
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 CFGPP_DEVICE void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+// One lane of a fully converged warp (elect.sync). Roles that issue TMA / tcgen05 instructions run their loops with the
+// WHOLE warp and predicate only the issue itself on this: the loop state then stays provably warp-uniform, so the
+// compiler keeps descriptors / coordinates in uniform registers instead of wrapping every UTCHMMA / UTMALDG in an
+// ELECT + R2UR + BRA.U.ANY "waterfall" loop (which made the single-thread MMA issuer the bottleneck of the main loop).
+CFGPP_DEVICE bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 CFGPP_DEVICE void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // D[tmem] (+)= A[smem desc] * B[smem desc], fp16/bf16 inputs, fp32 accumulate. One thread issues.

@@ -73,12 +73,12 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
   uint64_t* res_full_bar = bars + 2 * C::STAGES + 4;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 5);
 
-  const int warp_idx = threadIdx.x >> 5;
+  const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
   unsigned long long* tl = p.timeline ? p.timeline + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
 #define TL(slot) do { if (tl) tl[slot] = globaltimer_ns(); } while (0)
   if (threadIdx.x == 0) TL(0);
-  const int cta_rank = (CL > 1) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cta_rank = (CL > 1) ? __shfl_sync(0xffffffffu, static_cast<int>(cluster_ctarank()), 0) : 0;
   const int cluster_id = blockIdx.x / CL;
   const int num_clusters = gridDim.x / CL;
   const bool is_leader_cta = (cta_rank == 0);
@@ -116,7 +116,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
   __syncthreads();
   if constexpr (CL > 1) cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA signal
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
   if (threadIdx.x == 0) TL(1);
   pdl_launch_dependents();  // the next kernel may start its prologue on SMs this grid leaves
   pdl_wait();               // everything above overlapped the previous kernel's tail; its outputs are needed below
@@ -131,8 +131,8 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
   auto tile_n_blk = [&](int tile) { return tile / num_mg; };
 
   if (warp_idx == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
+    {
+      // ===================== TMA producer (whole warp walks the loop, one elected lane issues) ============
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -149,10 +149,12 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
         }
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (tile == cluster_id && kb == 0) TL(3);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          if constexpr (CL == 1) {
+          if (!elect_one()) {
+            // non-elected lanes only keep the loop state in step
+          } else if constexpr (CL == 1) {
+            if (tile == cluster_id && kb == 0) TL(3);
             mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
             if (p.conv) {
               const int tap = kb / p.cpb;
@@ -168,6 +170,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
             }
             tma_load_2d(sb, &map_b, &full_bar[stage], kb * BK, n_blk * BN);
           } else {
+            if (tile == cluster_id && kb == 0) TL(3);
             // both CTAs fill their own smem; all bytes are accounted on the leader's barrier (the MMA issuer's)
             if (is_leader_cta) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
             if (p.conv) {
@@ -192,8 +195,8 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
       }
     }
   } else if (warp_idx == 1) {
-    if (lane == 0 && is_leader_cta) {
-      // ===================== MMA issuer (pair: leader CTA only) =====================
+    if (is_leader_cta) {
+      // ===================== MMA issuer (pair: leader CTA only; whole warp loops, one elected lane issues) ==========
       constexpr uint32_t idesc = make_idesc_f16(BM * CL, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -206,29 +209,32 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
         const uint32_t d_tmem = tmem_base + as * C::ACC_STRIDE;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
-          if (it == 0 && kb == 0) TL(4);
-          if (it == 0 && kb == nkb - 1) TL(5);
-          if (kb == nkb - 1) TL(6);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_BYTES;
           const uint64_t a_desc = make_sdesc_sw128(a_addr, 1024, 0);
           const uint64_t b_desc = make_sdesc_sw128(b_addr, 1024, 0);
+          if (elect_one()) {
+            if (it == 0 && kb == 0) TL(4);
+            if (it == 0 && kb == nkb - 1) TL(5);
+            if (kb == nkb - 1) TL(6);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
-            if constexpr (CL == 1)
-              umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else
-              umma_f16_cg2(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-          // on retirement: free the smem slot (pair: in both CTAs) and, after the last k-block, publish the accumulator
-          if constexpr (CL == 1) {
-            umma_commit(&empty_bar[stage]);
-            if (kb == nkb - 1) umma_commit(&tmem_full_bar[as]);
-          } else {
-            umma_commit_cg2(&empty_bar[stage]);
-            if (kb == nkb - 1) umma_commit_cg2(&tmem_full_bar[as]);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
+              if constexpr (CL == 1)
+                umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else
+                umma_f16_cg2(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            // on retirement: free the smem slot (pair: in both CTAs) and, after the last k-block, publish the
+            // accumulator
+            if constexpr (CL == 1) {
+              umma_commit(&empty_bar[stage]);
+              if (kb == nkb - 1) umma_commit(&tmem_full_bar[as]);
+            } else {
+              umma_commit_cg2(&empty_bar[stage]);
+              if (kb == nkb - 1) umma_commit_cg2(&tmem_full_bar[as]);
+            }
           }
           if (++stage == C::STAGES) {
             stage = 0;
