@@ -6,12 +6,14 @@ PyTorch is used only as the owner of device memory and streams (raw pointers cro
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 from pathlib import Path
 
 import torch
 
-_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libcfgpp_b200.so"
+# CFGPP_B200_LIB points at an alternative build of the same library (A/B experiments with tools/build_variant.sh)
+_LIB_PATH = Path(os.environ.get("CFGPP_B200_LIB") or Path(__file__).resolve().parent / "lib" / "libcfgpp_b200.so")
 _lib = None
 
 

@@ -54,6 +54,9 @@ CFGPP_DEVICE uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok;
 }
+#ifndef CFGPP_MBAR_SLEEP_NS
+#define CFGPP_MBAR_SLEEP_NS 1000000
+#endif
 // Probe with a suspend-time hint: the thread may sleep in hardware for up to ~1 ms waiting for the phase, instead
 // of spinning through the issue stage (128 epilogue threads per SM wait for a whole main loop on tmem_full).
 CFGPP_DEVICE uint32_t mbar_try_wait_sleep(uint64_t* bar, uint32_t parity) {
@@ -65,7 +68,7 @@ CFGPP_DEVICE uint32_t mbar_try_wait_sleep(uint64_t* bar, uint32_t parity) {
       "selp.u32 %0, 1, 0, P1;\n\t"
       "}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(1000000)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(CFGPP_MBAR_SLEEP_NS)
       : "memory");
   return ok;
 }
@@ -74,7 +77,11 @@ CFGPP_DEVICE uint32_t mbar_try_wait_sleep(uint64_t* bar, uint32_t parity) {
 CFGPP_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+#if CFGPP_MBAR_SLEEP_NS > 0
   while (!mbar_try_wait_sleep(bar, parity)) {
+#else
+  while (!mbar_try_wait(bar, parity)) {
+#endif
     if (clock64() - t0 > 4000000000LL) {
       printf("cfgpp: mbarrier wait timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x,
              smem_u32(bar), parity);

@@ -1,12 +1,14 @@
 // cfgpp_b200 — persistent, warp-specialised tcgen05 GEMM / implicit-GEMM conv3x3 kernel for sm_100a.
 // See gemm.cuh for the operator contract. Structure per CTA (256 threads, 1 CTA / SM, persistent over tiles):
-//   warp 0 lane 0 : TMA producer  (A tile 128x64, B tile BNx64 per stage, 128B swizzle, mbarrier complete_tx)
-//   warp 1 lane 0 : MMA issuer    (tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16 x4 per stage)
-//   warp 2        : TMEM allocator
-//   warps 4..7    : epilogue      (tcgen05.ld 32x32b -> bias/addend/GEGLU -> fp16 global stores)
+//   warps 0..3 : epilogue      (tcgen05.ld 32x32b -> bias/addend/GEGLU -> fp16 smem staging -> TMA store)
+//   warp 4     : TMA producer  (A tile 128x64, B tile BNx64 per stage, 128B swizzle, mbarrier complete_tx)
+//   warp 5     : MMA issuer    (tcgen05.mma kind::f16, M=128 (256 for a CTA pair), N=BN, K=16 x4 per stage)
+//   warp 6     : TMEM allocator
+// The producer and issuer warps run their loops warp-wide and issue from one elected lane (see elect_one()).
 // Pipelines: smem ring full/empty (TMA <-> MMA) and a 2-deep TMEM accumulator ring full/empty (MMA <-> epilogue),
 // so the epilogue of tile i overlaps the main loop of tile i+1.
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "gemm.cuh"
@@ -20,6 +22,23 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kThreads = 256;
+// Warp roles. The SM sub-partition arbiter serves the highest warp id first (warps w and w + 4 share a sub-partition),
+// so the two issue warps sit ABOVE the epilogue warps: a TMA / tcgen05.mma issue slot is never queued behind the
+// ALU-heavy epilogue of the previous tile. Epilogue warp w owns TMEM lane quarter w % 4.
+#ifndef CFGPP_GEMM_HI_ISSUER
+#define CFGPP_GEMM_HI_ISSUER 1
+#endif
+#if CFGPP_GEMM_HI_ISSUER
+constexpr int kEpiWarp0 = 0;      // warps 0..3
+constexpr int kProducerWarp = 4;
+constexpr int kMmaWarp = 5;
+constexpr int kAllocWarp = 6;
+#else
+constexpr int kEpiWarp0 = 4;      // warps 4..7
+constexpr int kProducerWarp = 0;
+constexpr int kMmaWarp = 1;
+constexpr int kAllocWarp = 2;
+#endif
 constexpr int A_BYTES = BM * BK * 2;
 
 template <int BN, bool GEGLU, int CL = 1>
@@ -83,14 +102,14 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
   const int num_clusters = gridDim.x / CL;
   const bool is_leader_cta = (cta_rank == 0);
 
-  if (warp_idx == 0 && lane == 0) {
+  if (warp_idx == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_a2);
     tma_prefetch_desc(&map_b);
     tma_prefetch_desc(&map_out);
     tma_prefetch_desc(&map_res);
   }
-  if (warp_idx == 1 && lane == 0) {
+  if (warp_idx == kMmaWarp && lane == 0) {
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -103,7 +122,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
     fence_barrier_init();
   }
   if constexpr (CL > 1) cluster_sync_all();  // both CTAs resident before the pair-wide TMEM allocation
-  if (warp_idx == 2) {
+  if (warp_idx == kAllocWarp) {
     if constexpr (CL == 2) {
       tmem_alloc_cg2(tmem_ptr_smem, C::TMEM_COLS);
       tmem_relinquish_cg2();
@@ -130,7 +149,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
   auto tile_m_blk = [&](int tile) { return (tile % num_mg) * CL + cta_rank; };
   auto tile_n_blk = [&](int tile) { return tile / num_mg; };
 
-  if (warp_idx == 0) {
+  if (warp_idx == kProducerWarp) {
     {
       // ===================== TMA producer (whole warp walks the loop, one elected lane issues) ============
       int stage = 0;
@@ -194,7 +213,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
         }
       }
     }
-  } else if (warp_idx == 1) {
+  } else if (warp_idx == kMmaWarp) {
     if (is_leader_cta) {
       // ===================== MMA issuer (pair: leader CTA only; whole warp loops, one elected lane issues) ==========
       constexpr uint32_t idesc = make_idesc_f16(BM * CL, BN, 0, 0);
@@ -243,15 +262,15 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
         }
       }
     }
-  } else if (warp_idx >= 4) {
+  } else if (warp_idx >= kEpiWarp0 && warp_idx < kEpiWarp0 + 4) {
     // ===================== epilogue =====================
     // TMEM -> registers -> (bias / time-embedding row / residual / GEGLU) -> fp16 into the swizzled smem staging
     // tile -> TMA store (coalesced, clipped at the M / N edges by the hardware). The full residual tile is TMA-loaded
     // into the same staging area while the main loop of the tile runs, and overwritten in place.
-    const int q = warp_idx - 4;  // == warp_idx % 4: the TMEM lane quarter this warp may access
+    const int q = warp_idx - kEpiWarp0;  // == warp_idx % 4: the TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const bool leader = (threadIdx.x == 128);
+    const bool leader = (threadIdx.x == kEpiWarp0 * 32);
     const bool full_res = (p.addend != nullptr) && (p.add_rows_per_group <= 1);
     const int sw = (row >> 1) & 3;  // 64B swizzle: 16-byte chunk index ^= (row / 2) % 4
     uint8_t* my_row = epi_smem + row * 64;
@@ -288,7 +307,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
         for (int c = row; c < ncols; c += 128) {
           const int n = n_base + c;
           const bool ok = n < p.N;
-          if (p.bias) s_bias[c] = ok ? p.bias[n] : __float2half(0.f);
+          s_bias[c] = (p.bias && ok) ? p.bias[n] : __float2half(0.f);
           if (temb_staged) s_temb[c] = ok ? add_row[n] : __float2half(0.f);
           if (p.stats_in) {
             s_lns[c] = ok ? p.ln_s[n] : 0.f;
@@ -316,100 +335,159 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
       tc_fence_after();
       if (full_res) mbar_wait(res_full_bar, it & 1);
       named_bar_sync(1, 128);  // staged vectors visible to all epilogue threads
+      if (leader && it == 0) TL(13);
       const uint32_t t_base = tmem_base + as * C::ACC_STRIDE + lane_off;
 
+      // The arithmetic variant (LayerNorm fold / kind of addend / row statistics) is chosen ONCE per tile and the chunk
+      // loop is instantiated per variant: with the flags tested inside the unrolled loop the compiler unswitched every
+      // 8-column group into a tree of ~140 branches spread over 50 KB of code, and the epilogue ran at ~1 us per
+      // 32-column chunk (instruction fetch bound) instead of ~0.3 us.
       if constexpr (!GEGLU) {
+        auto chunks = [&](auto ln_c, auto add_c, auto st_c) {
+          constexpr bool LN = decltype(ln_c)::value;
+          constexpr int ADD = decltype(add_c)::value;  // 0 none, 1 full residual tile, 2 staged row, 3 per-row global
+          constexpr bool ST = decltype(st_c)::value;
 #pragma unroll 1
-        for (int j = 0; j < C::EPI_SUB; ++j) {
-          uint32_t v[32];
-          tmem_ld_x32(t_base + j * 32, v);
-          tmem_ld_wait();
-          const int n0 = n_blk * BN + j * 32;
-          uint8_t* srow = my_row + j * C::EPI_SUB_BYTES;
-          uint32_t o[16];
+          for (int j = 0; j < C::EPI_SUB; ++j) {
+            uint32_t v[32];
+            tmem_ld_x32(t_base + j * 32, v);
+            tmem_ld_wait();
+            const int n0 = n_blk * BN + j * 32;
+            uint8_t* srow = my_row + j * C::EPI_SUB_BYTES;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint4 r4 = make_uint4(0, 0, 0, 0);
-            if (full_res) r4 = *reinterpret_cast<const uint4*>(srow + ((c ^ sw) << 4));
-            const __half2* rh = reinterpret_cast<const __half2*>(&r4);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int jj = c * 4 + e;  // half2 index within the 32-column chunk
-              float x0 = __uint_as_float(v[2 * jj]), x1 = __uint_as_float(v[2 * jj + 1]);
-              if (p.stats_in) {
-                x0 = x0 * ln_rstd - ln_rm * s_lns[j * 32 + 2 * jj] + s_lnt[j * 32 + 2 * jj];
-                x1 = x1 * ln_rstd - ln_rm * s_lns[j * 32 + 2 * jj + 1] + s_lnt[j * 32 + 2 * jj + 1];
-              } else if (p.bias) {
-                const __half2 b = *reinterpret_cast<const __half2*>(s_bias + j * 32 + 2 * jj);
-                x0 += __low2float(b);
-                x1 += __high2float(b);
+            for (int c = 0; c < 4; ++c) {  // 8 columns = one 16-byte piece of the output row
+              const int col = j * 32 + c * 8;
+              uint4 r4 = make_uint4(0, 0, 0, 0), b4 = make_uint4(0, 0, 0, 0);
+              if constexpr (ADD == 1) r4 = *reinterpret_cast<const uint4*>(srow + ((c ^ sw) << 4));
+              if constexpr (ADD == 2) r4 = *reinterpret_cast<const uint4*>(s_temb + col);
+              if constexpr (!LN) b4 = *reinterpret_cast<const uint4*>(s_bias + col);  // zeros when there is no bias
+              const __half2* rh = reinterpret_cast<const __half2*>(&r4);
+              const __half2* bh = reinterpret_cast<const __half2*>(&b4);
+              float sv[8], tv[8];
+              if constexpr (LN) {
+                *reinterpret_cast<float4*>(&sv[0]) = *reinterpret_cast<const float4*>(s_lns + col);
+                *reinterpret_cast<float4*>(&sv[4]) = *reinterpret_cast<const float4*>(s_lns + col + 4);
+                *reinterpret_cast<float4*>(&tv[0]) = *reinterpret_cast<const float4*>(s_lnt + col);
+                *reinterpret_cast<float4*>(&tv[4]) = *reinterpret_cast<const float4*>(s_lnt + col + 4);
               }
-              __half2 t = __floats2half2_rn(x0, x1);
-              if (full_res) {
-                t = __floats2half2_rn(__low2float(t) + __low2float(rh[e]), __high2float(t) + __high2float(rh[e]));
-              } else if (add_row) {
-                float a0 = 0.f, a1 = 0.f;
-                if (temb_staged) {
-                  const __half2 a = *reinterpret_cast<const __half2*>(s_temb + j * 32 + 2 * jj);
-                  a0 = __low2float(a);
-                  a1 = __high2float(a);
-                } else {  // tile spans several samples (tiny latents): per-row global loads
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int jj = c * 4 + e;  // half2 index within the 32-column chunk
+                float x0 = __uint_as_float(v[2 * jj]), x1 = __uint_as_float(v[2 * jj + 1]);
+                if constexpr (LN) {
+                  x0 = x0 * ln_rstd - ln_rm * sv[2 * e] + tv[2 * e];
+                  x1 = x1 * ln_rstd - ln_rm * sv[2 * e + 1] + tv[2 * e + 1];
+                } else {
+                  x0 += __low2float(bh[e]);
+                  x1 += __high2float(bh[e]);
+                }
+                __half2 t = __floats2half2_rn(x0, x1);
+                if constexpr (ADD == 1 || ADD == 2) {
+                  t = __floats2half2_rn(__low2float(t) + __low2float(rh[e]), __high2float(t) + __high2float(rh[e]));
+                } else if constexpr (ADD == 3) {  // tile spans several samples (tiny latents): per-row global loads
+                  float a0 = 0.f, a1 = 0.f;
                   if (n0 + 2 * jj < p.N) a0 = __half2float(add_row[n0 + 2 * jj]);
                   if (n0 + 2 * jj + 1 < p.N) a1 = __half2float(add_row[n0 + 2 * jj + 1]);
+                  t = __floats2half2_rn(__low2float(t) + a0, __high2float(t) + a1);
                 }
-                t = __floats2half2_rn(__low2float(t) + a0, __high2float(t) + a1);
+                if constexpr (ST) {
+                  const float f0 = __low2float(t), f1 = __high2float(t);
+                  ps += f0 + f1;
+                  pss += f0 * f0 + f1 * f1;
+                }
+                o[e] = *reinterpret_cast<uint32_t*>(&t);
               }
-              if (p.stats_out) {
-                const float f0 = __low2float(t), f1 = __high2float(t);
-                ps += f0 + f1;
-                pss += f0 * f0 + f1 * f1;
-              }
-              o[jj] = *reinterpret_cast<uint32_t*>(&t);
+              *reinterpret_cast<uint4*>(srow + ((c ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
             }
-            *reinterpret_cast<uint4*>(srow + ((c ^ sw) << 4)) = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+          }
+        };
+        using T = std::true_type;
+        using F = std::false_type;
+        const int add_mode = full_res ? 1 : (add_row == nullptr ? 0 : (temb_staged ? 2 : 3));
+        if (p.stats_in) {  // LayerNorm-fold consumer: bias is inside t_n; no addend, no statistics (host-checked)
+          chunks(T{}, std::integral_constant<int, 0>{}, F{});
+        } else if (p.stats_out) {
+          switch (add_mode) {
+            case 0: chunks(F{}, std::integral_constant<int, 0>{}, T{}); break;
+            case 1: chunks(F{}, std::integral_constant<int, 1>{}, T{}); break;
+            case 2: chunks(F{}, std::integral_constant<int, 2>{}, T{}); break;
+            default: chunks(F{}, std::integral_constant<int, 3>{}, T{}); break;
+          }
+        } else {
+          switch (add_mode) {
+            case 0: chunks(F{}, std::integral_constant<int, 0>{}, F{}); break;
+            case 1: chunks(F{}, std::integral_constant<int, 1>{}, F{}); break;
+            case 2: chunks(F{}, std::integral_constant<int, 2>{}, F{}); break;
+            default: chunks(F{}, std::integral_constant<int, 3>{}, F{}); break;
           }
         }
         if (p.stats_out && m < p.M)
           *reinterpret_cast<float2*>(p.stats_out + (static_cast<size_t>(n_blk) * p.M + m) * 2) = make_float2(ps, pss);
       } else {
         // value columns [0,128), gate columns [128,256) of this tile -> 128 output columns
+        auto chunks = [&](auto ln_c) {
+          constexpr bool LN = decltype(ln_c)::value;
 #pragma unroll 1
-        for (int j = 0; j < C::EPI_SUB; ++j) {
-          uint32_t va[32], vg[32];
-          tmem_ld_x32(t_base + j * 32, va);
-          tmem_ld_x32(t_base + BN / 2 + j * 32, vg);
-          tmem_ld_wait();
-          uint8_t* srow = my_row + j * C::EPI_SUB_BYTES;
-          uint32_t o[16];
+          for (int j = 0; j < C::EPI_SUB; ++j) {
+            uint32_t va[32], vg[32];
+            tmem_ld_x32(t_base + j * 32, va);
+            tmem_ld_x32(t_base + BN / 2 + j * 32, vg);
+            tmem_ld_wait();
+            uint8_t* srow = my_row + j * C::EPI_SUB_BYTES;
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            float a0 = __uint_as_float(va[2 * jj]), a1 = __uint_as_float(va[2 * jj + 1]);
-            float g0 = __uint_as_float(vg[2 * jj]), g1 = __uint_as_float(vg[2 * jj + 1]);
-            if (p.stats_in) {
-              const int ia = j * 32 + 2 * jj, ig = BN / 2 + j * 32 + 2 * jj;
-              a0 = a0 * ln_rstd - ln_rm * s_lns[ia] + s_lnt[ia];
-              a1 = a1 * ln_rstd - ln_rm * s_lns[ia + 1] + s_lnt[ia + 1];
-              g0 = g0 * ln_rstd - ln_rm * s_lns[ig] + s_lnt[ig];
-              g1 = g1 * ln_rstd - ln_rm * s_lns[ig + 1] + s_lnt[ig + 1];
-            } else if (p.bias) {
-              const __half2 ba = *reinterpret_cast<const __half2*>(s_bias + j * 32 + 2 * jj);
-              const __half2 bg = *reinterpret_cast<const __half2*>(s_bias + BN / 2 + j * 32 + 2 * jj);
-              a0 += __low2float(ba);
-              a1 += __high2float(ba);
-              g0 += __low2float(bg);
-              g1 += __high2float(bg);
+            for (int c = 0; c < 4; ++c) {
+              const int ia = j * 32 + c * 8, ig = BN / 2 + ia;
+              uint4 ba4 = make_uint4(0, 0, 0, 0), bg4 = make_uint4(0, 0, 0, 0);
+              float sa[8], ta[8], sg[8], tg[8];
+              if constexpr (LN) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  *reinterpret_cast<float4*>(&sa[4 * h]) = *reinterpret_cast<const float4*>(s_lns + ia + 4 * h);
+                  *reinterpret_cast<float4*>(&ta[4 * h]) = *reinterpret_cast<const float4*>(s_lnt + ia + 4 * h);
+                  *reinterpret_cast<float4*>(&sg[4 * h]) = *reinterpret_cast<const float4*>(s_lns + ig + 4 * h);
+                  *reinterpret_cast<float4*>(&tg[4 * h]) = *reinterpret_cast<const float4*>(s_lnt + ig + 4 * h);
+                }
+              } else {
+                ba4 = *reinterpret_cast<const uint4*>(s_bias + ia);  // zeros when there is no bias
+                bg4 = *reinterpret_cast<const uint4*>(s_bias + ig);
+              }
+              const __half2* bah = reinterpret_cast<const __half2*>(&ba4);
+              const __half2* bgh = reinterpret_cast<const __half2*>(&bg4);
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int jj = c * 4 + e;
+                float a0 = __uint_as_float(va[2 * jj]), a1 = __uint_as_float(va[2 * jj + 1]);
+                float g0 = __uint_as_float(vg[2 * jj]), g1 = __uint_as_float(vg[2 * jj + 1]);
+                if constexpr (LN) {
+                  a0 = a0 * ln_rstd - ln_rm * sa[2 * e] + ta[2 * e];
+                  a1 = a1 * ln_rstd - ln_rm * sa[2 * e + 1] + ta[2 * e + 1];
+                  g0 = g0 * ln_rstd - ln_rm * sg[2 * e] + tg[2 * e];
+                  g1 = g1 * ln_rstd - ln_rm * sg[2 * e + 1] + tg[2 * e + 1];
+                } else {
+                  a0 += __low2float(bah[e]);
+                  a1 += __high2float(bah[e]);
+                  g0 += __low2float(bgh[e]);
+                  g1 += __high2float(bgh[e]);
+                }
+                const __half2 ah = __floats2half2_rn(a0, a1);
+                const __half2 gh = __floats2half2_rn(g0, g1);
+                const __half2 ge = __floats2half2_rn(gelu_erf_f(__low2float(gh)), gelu_erf_f(__high2float(gh)));
+                const __half2 r =
+                    __floats2half2_rn(__low2float(ah) * __low2float(ge), __high2float(ah) * __high2float(ge));
+                o[e] = *reinterpret_cast<const uint32_t*>(&r);
+              }
+              *reinterpret_cast<uint4*>(srow + ((c ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
             }
-            const __half2 ah = __floats2half2_rn(a0, a1);
-            const __half2 gh = __floats2half2_rn(g0, g1);
-            const __half2 ge = __floats2half2_rn(gelu_erf_f(__low2float(gh)), gelu_erf_f(__high2float(gh)));
-            const __half2 r = __floats2half2_rn(__low2float(ah) * __low2float(ge), __high2float(ah) * __high2float(ge));
-            o[jj] = *reinterpret_cast<const uint32_t*>(&r);
           }
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            *reinterpret_cast<uint4*>(srow + ((c ^ sw) << 4)) = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
-        }
+        };
+        if (p.stats_in)
+          chunks(std::true_type{});
+        else
+          chunks(std::false_type{});
       }
+      if (leader && it == 0) TL(14);
       tc_fence_before();
       if constexpr (CL == 1) mbar_arrive(&tmem_empty_bar[as]);  // accumulator drained: MMA may reuse this stage
       fence_proxy_async_smem();  // staging tile written by the generic proxy -> visible to TMA
@@ -435,7 +513,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
   tc_fence_before();
   __syncthreads();
   if constexpr (CL > 1) cluster_sync_all();  // no CTA leaves while its peer may still multicast / arrive into it
-  if (warp_idx == 2) {
+  if (warp_idx == kAllocWarp) {
     tc_fence_after();
     if constexpr (CL == 2)
       tmem_dealloc_cg2(tmem_base, C::TMEM_COLS);
@@ -580,6 +658,9 @@ GemmOp make_conv3x3_op(const __half* x, int B, int H, int W, int Cin, const __ha
 }
 
 void run_gemm_op(const GemmOp& op, cudaStream_t stream) {
+  CFGPP_REQUIRE(!(op.p.stats_in && (op.p.addend || op.p.stats_out)),
+                "a LayerNorm-fold consumer GEMM takes no addend and emits no row statistics");
+  CFGPP_REQUIRE(!(op.p.geglu && (op.p.addend || op.p.stats_out)), "the GEGLU epilogue takes no addend / statistics");
   if (op.p.geglu) return launch<256, true>(op, stream);
   switch (op.bn) {
     case 64: return launch<64, false>(op, stream);

@@ -13,9 +13,10 @@ from cfgpp_b200 import _native as nv  # noqa: E402
 dev = torch.device("cuda:0")
 lib = nv.load()
 names = ["entry", "prologue_done", "pdl_wait_done", "first_tma", "first_full", "tile0_lastkb", "lasttile_lastkb",
-         "epi0_start", "epi0_store", "epiL_start", "epiL_store", "exit"]
+         "epi0_start", "epi0_store", "epiL_start", "epiL_store", "exit", "ntiles", "epi0_allwarps", "epi0_loopdone"]
 for (M, N, K, res, bn) in [(4096, 1280, 1280, False, 0), (4096, 1280, 1280, True, 0), (4096, 1280, 5120, True, 0),
-                           (4096, 3840, 1280, False, 0), (16384, 640, 640, True, 0), (8192, 8192, 8192, False, 256)]:
+                           (4096, 3840, 1280, False, 0), (16384, 640, 640, True, 0), (8192, 8192, 8192, False, 256)
+                           ][: int(sys.argv[1]) if len(sys.argv) > 1 else None]:
     g = torch.Generator().manual_seed(0)
     a = torch.randn(M, K, generator=g).half().to(dev)
     w = (torch.randn(N, K, generator=g) * K ** -0.5).half().to(dev)
@@ -32,6 +33,8 @@ for (M, N, K, res, bn) in [(4096, 1280, 1280, False, 0), (4096, 1280, 1280, True
     print(f"--- GEMM M={M} N={N} K={K} residual={res} grid={grid.value}  kernel span {(t[:, 11].max() - t0)/1e3:.1f} us "
           f"tiles/CTA max {t[:, 12].max()} min {t[:, 12].min()}")
     for i, nm in enumerate(names):
+        if nm == 'ntiles':
+            continue
         col = t[:, i]
         valid = col > 0
         if valid.any():
