@@ -40,7 +40,7 @@ struct GemmParams {
   // t_n = sum_k beta_k W_nk (+ bias_n). The GEMM that PRODUCES h writes per-row partial (sum, sum of squares) of its
   // fp16 output, one slot per N block (deterministic, no atomics); the GEMM that CONSUMES LN(h) runs on h directly
   // with the folded weight and applies the row / column corrections in its epilogue.
-  float* stats_out;        // producer: [num_n_blocks][M] float2, or null
+  float* stats_out;        // producer: [2 * num_n_blocks][M] float2 (two column halves per N block), or null
   const float* stats_in;   // consumer: [ln_parts][M] float2, or null
   int ln_parts;
   float ln_inv_c, ln_eps;

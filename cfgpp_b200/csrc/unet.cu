@@ -431,7 +431,7 @@ Unet::Act Unet::build_transformer(const std::string& prefix, Act x, int H, int W
   Scratch* s_ff = scratch(btag_ + "ff", M * 4 * C);
   Scratch* s_stats[3];
   for (int i = 0; i < 3; ++i)  // [16 N blocks][M] float2 partial row statistics (LayerNorm fold)
-    s_stats[i] = scratch(btag_ + "lnstats" + std::to_string(i), static_cast<size_t>(16) * M * 2 * 2);
+    s_stats[i] = scratch(btag_ + "lnstats" + std::to_string(i), static_cast<size_t>(32) * M * 2 * 2);
   __half* out = g_dry ? nullptr : alloc_act(M * C);
   const int Mkv = bnb_ * n_ctx_;
   if (g_dry) {
@@ -473,8 +473,9 @@ Unet::Act Unet::build_transformer(const std::string& prefix, Act x, int H, int W
           }
       }
       CFGPP_REQUIRE(C % op.bn == 0 && op.p.num_n_blocks <= 16, "LayerNorm fold: no tile width divides C");
+      // two partial sums per N block: the epilogue splits a tile's columns between two warps per row
       op.p.stats_out = stats[slot];
-      parts[slot] = op.p.num_n_blocks;
+      parts[slot] = 2 * op.p.num_n_blocks;
     }
     return op;
   };
