@@ -104,13 +104,29 @@ __global__ void gn_apply_kernel(GnSrc src, int HW, int C, int px_per_block, cons
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float s_mean[GROUPS], s_rstd[GROUPS];
+  __shared__ float2 s_part[8][GROUPS];
   const int b = blockIdx.y;
+  // Cross-chunk reduction of the partial sums, spread over 8 x 32 threads (each sums every 8th chunk, loads
+  // independent), then combined in a fixed order: a single thread per group walking all (up to 128) chunks exposed
+  // ~10 us of serialised L2 latency at the head of EVERY block.
+  for (int idx = threadIdx.x; idx < 8 * GROUPS; idx += blockDim.x) {
+    const int g = idx & (GROUPS - 1), part = idx / GROUPS;
+    float a = 0.f, q = 0.f;
+    const float* src_p = partial + (static_cast<size_t>(b) * nchunk * GROUPS + g) * 2;
+    for (int i = part; i < nchunk; i += 8) {
+      const float2 v = *reinterpret_cast<const float2*>(src_p + static_cast<size_t>(i) * GROUPS * 2);
+      a += v.x;
+      q += v.y;
+    }
+    s_part[part][g] = make_float2(a, q);
+  }
+  __syncthreads();
   if (threadIdx.x < GROUPS) {
     float a = 0.f, q = 0.f;
-    const float* src_p = partial + (static_cast<size_t>(b) * nchunk * GROUPS + threadIdx.x) * 2;
-    for (int i = 0; i < nchunk; ++i) {
-      a += src_p[static_cast<size_t>(i) * GROUPS * 2];
-      q += src_p[static_cast<size_t>(i) * GROUPS * 2 + 1];
+#pragma unroll
+    for (int part = 0; part < 8; ++part) {
+      a += s_part[part][threadIdx.x].x;
+      q += s_part[part][threadIdx.x].y;
     }
     const float n = static_cast<float>(HW) * (C / GROUPS);
     const float mean = a / n;
