@@ -759,9 +759,12 @@ void Unet::prepare(int batch, int h_lat, int w_lat) {
     }
 
     // ---- body ----
-    // The unconditional and the conditional halves of the UNet batch never interact before the CFG++ mix, so each
-    // gets its own launch plan (rows [0,B) and [B,2B)); inside the captured graph the two run on forked streams,
-    // letting one half's GEMM fill / drain, norms and attention overlap the other half's tensor work.
+    // The unconditional and the conditional halves of the UNet batch never interact before the CFG++ mix, so the body
+    // can be built as two launch plans (rows [0,B) and [B,2B)) that run on forked streams inside the captured graph,
+    // one half's GEMM fill / drain, norms and attention overlapping the other half's tensor work (CFGPP_SPLIT=1). That
+    // won 4 % while a GEMM launch lost ~10 us to fill / drain / epilogue; since the issue-loop and epilogue rewrites the
+    // full-batch kernels are faster per row and the single plan is ahead by ~1 % (tools/ab_split.sh), so it is the
+    // default.
     const int HW0 = H_ * W_;
     Act h0{g_dry ? nullptr : alloc_act(static_cast<size_t>(NB_) * HW0 * C0), C0};
     if (g_dry) workspace_bytes_ += 2 * static_cast<size_t>(NB_) * HW0 * C0 * sizeof(__half);
@@ -896,8 +899,8 @@ void Unet::run_body(cudaStream_t stream, bool concurrent) {
 bool Unet::split_disabled() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("CFGPP_NO_SPLIT");
-    v = (e && e[0] == '1') ? 1 : 0;
+    const char* e = getenv("CFGPP_SPLIT");
+    v = (e && e[0] == '1') ? 0 : 1;
   }
   return v == 1;
 }

@@ -1,3 +1,5 @@
-timeout 900 python -m pytest tests/test_gpu_samplers.py tests/test_gpu_unet.py -m gpu -x -q 2>&1 | tail -n 6
-echo "--- NO SPLIT"; CFGPP_NO_SPLIT=1 bash tools/run_diag.sh bench_unet 2>&1 | grep -E "native"
-echo "--- SPLIT"; bash tools/run_diag.sh bench_unet 2>&1 | grep -E "native"
+# same-box A/B: uncond / cond halves as two concurrent graph branches (CFGPP_SPLIT=1) vs one full-batch body (default)
+for rep in 1 2 3; do
+echo "--- SPLIT"; CFGPP_SPLIT=1 bash tools/run_diag.sh bench_unet 2>&1 | grep -E "native fused"
+echo "--- NO SPLIT"; bash tools/run_diag.sh bench_unet 2>&1 | grep -E "native fused"
+done
