@@ -473,7 +473,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
                 }
                 const __half2 ah = __floats2half2_rn(a0, a1);
                 const __half2 gh = __floats2half2_rn(g0, g1);
-                const __half2 ge = __floats2half2_rn(gelu_erf_f(__low2float(gh)), gelu_erf_f(__high2float(gh)));
+                const __half2 ge = __floats2half2_rn(gelu_erf_fast_f(__low2float(gh)), gelu_erf_fast_f(__high2float(gh)));
                 const __half2 r =
                     __floats2half2_rn(__low2float(ah) * __low2float(ge), __high2float(ah) * __high2float(ge));
                 o[e] = *reinterpret_cast<const uint32_t*>(&r);
