@@ -37,9 +37,8 @@ LATENT = 128
 METRIC = "images/sec (device-timed) SDXL 1024x1024 NFE=50 ddim_cfg++"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, mean over the 12 consecutive
 # gemm_kernel launches of a 1280-channel transformer block in one `ncu --set full` capture (cold L2: an upper bound;
-# it equals the algorithmic A + W + residual bytes, i.e. no re-reads) — profiles/r01_v3_ncu_full.md (per-branch
-# launches: half the rows of the v2 capture, hence the smaller figure)
-NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 20.66e6
+# it equals the algorithmic A + W + residual bytes, i.e. no re-reads) — profiles/r01_v3_ncu_full.md
+NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 33.45e6
 NCU_TRAFFIC_SOURCE = "ncu --set full, gpurun_out/prof_gemm.ncu-rep (round 1 v3), summarised in profiles/r01_v3_ncu_full.md"
 
 
