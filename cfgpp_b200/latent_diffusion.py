@@ -4,6 +4,9 @@ Mirror of the reference's `latent_diffusion.py` solver API for the hot path: reg
 base (:54-241: `alpha`, `get_text_embed`, `encode`, `decode`, `predict_noise`, `inversion`, `initialize_latent`),
 `ddim_cfg++` (:621-679) and `ddim_inversion_cfg++` (:882-957). Same names, argument meaning and errors; the UNet
 forward, CFG++ mix and DDIM update run in hand-written sm_100a CUDA behind include/cfgpp_b200.h.
+SURVEY §8 f1 (the rest of the CFG++ `--method` surface): `ddim_edit_cfg++` (:959-1010) on the same fused step modes;
+`euler_cfg++` (:682-724), `euler_a_cfg++` (:727-768), `dpm++_2s_a_cfg++` (:771-827), `dpm++_2m_cfg++` (:830-879) with
+the native UNet behind `predict_noise` and their few elementwise update ops in torch (kdiffusion.py).
 
 dtype note (reference promotion rules): `ddim_cfg++` keeps an fp32 latent state (zT is a fp32
 `torch.randn`); `ddim_inversion_cfg++` starts from the fp16 VAE latent, so both its inversion loop and the following
@@ -15,6 +18,7 @@ from typing import Any, Optional
 
 import torch
 
+from . import kdiffusion as K
 from . import schedule as S
 from .conditioning import LatentPreviewDecoder, SyntheticTextEncoder
 from .config import UNetConfig, sd15_config
@@ -41,7 +45,7 @@ def get_solver(name: str, **kwargs):
 ########################
 
 
-class StableDiffusion():
+class StableDiffusion(K.KDiffusionMixin):
     def __init__(self,
                  solver_config,
                  model_key: str = "runwayml/stable-diffusion-v1-5",
@@ -185,6 +189,81 @@ class InversionDDIMCFGpp(BaseDDIMCFGpp):
         img = self.decode(z0t)
         img = (img / 2 + 0.5).clamp(0, 1)
         return img.detach().cpu()
+
+
+@register_solver("ddim_edit_cfg++")
+class EditWordSwapDDIMCFGpp(InversionDDIMCFGpp):
+    """Editing via WordSwap after inversion: CFG++ inversion under the source prompt, CFG++ sampling under the target
+    prompt (latent_diffusion.py:959-1010). Both loops run as fused trajectories with an fp16 state."""
+
+    def sample(self, src_img, cfg_guidance=7.5, prompt=["", "", ""], callback_fn=None, **kwargs):
+        uc, src_c = self.get_text_embed(null_prompt=prompt[0], prompt=prompt[1])
+        _, tgt_c = self.get_text_embed(null_prompt=prompt[0], prompt=prompt[2])
+        zt = self.initialize_latent(method='ddim', src_img=src_img, uc=uc, c=src_c, cfg_guidance=cfg_guidance)
+        z0t = self.reverse_process(uc, tgt_c, cfg_guidance, zt, callback_fn)
+        img = self.decode(z0t)
+        img = (img / 2 + 0.5).clamp(0, 1)
+        return img.detach().cpu()
+
+
+class _KarrasCFGpp(StableDiffusion):
+    """Shared front / back end of the VE-cast samplers: Karras sigmas over the NFE steps, x ~ N(0, sigma_0^2 + 1) in
+    fp16, decode of either the last Tweedie estimate or the final state (latent_diffusion.py:688-697, 720-724)."""
+    adopt_callback = True
+    decode_state = False  # True: decode x (dpm++ variants), False: decode the last denoised (euler variants)
+
+    def _loop(self, x, sigmas, cfg_guidance, cond, callback_fn):
+        raise NotImplementedError
+
+    def karras_sigmas(self):
+        ts = self.total_sigmas()
+        return K.get_sigmas_karras(len(self.scheduler.timesteps), ts.min(), ts.max(), rho=7.)
+
+    @torch.no_grad()
+    def reverse_process(self, uc, c, cfg_guidance, x=None, callback_fn=None):
+        sigmas = self.karras_sigmas()
+        if x is None:
+            x = self.initialize_latent(method="random_kdiffusion", sigmas=sigmas,
+                                       latent_dim=(1, 4, self.cfg.sample_size, self.cfg.sample_size))
+        return self._loop(x.to(torch.float16), sigmas, cfg_guidance, (uc, c), callback_fn)
+
+    def sample(self, cfg_guidance, prompt=["", ""], callback_fn=None, **kwargs):
+        uc, c = self.get_text_embed(null_prompt=prompt[0], prompt=prompt[1])
+        denoised, x = self.reverse_process(uc, c, cfg_guidance, kwargs.get('xT'), callback_fn)
+        img = self.decode(x if self.decode_state else denoised)
+        img = (img / 2 + 0.5).clamp(0, 1)
+        return img.detach().cpu()
+
+
+@register_solver("euler_cfg++")
+class EulerCFGppSolver(_KarrasCFGpp):
+    def _loop(self, x, sigmas, cfg_guidance, cond, callback_fn):
+        # the reference binds the callback's return values to unused names here (:713-719): nothing is adopted
+        return K.euler_cfgpp_loop(self, x, sigmas, cfg_guidance, cond, callback_fn, adopt_callback=False)
+
+
+@register_solver("euler_a_cfg++")
+class EulerAncestralCFGppSolver(_KarrasCFGpp):
+    """Karras Euler (VE casted) + ancestral sampling."""
+    def _loop(self, x, sigmas, cfg_guidance, cond, callback_fn):
+        return K.euler_cfgpp_loop(self, x, sigmas, cfg_guidance, cond, callback_fn, ancestral=True,
+                                  adopt_callback=False)
+
+
+@register_solver("dpm++_2s_a_cfg++")
+class DPMpp2sAncestralCFGppSolver(_KarrasCFGpp):
+    decode_state = True
+
+    def _loop(self, x, sigmas, cfg_guidance, cond, callback_fn):
+        return K.dpmpp_2s_a_cfgpp_loop(self, x, sigmas, cfg_guidance, cond, callback_fn)
+
+
+@register_solver("dpm++_2m_cfg++")
+class DPMpp2mCFGppSolver(_KarrasCFGpp):
+    decode_state = True
+
+    def _loop(self, x, sigmas, cfg_guidance, cond, callback_fn):
+        return K.dpmpp_2m_cfgpp_karras_loop(self, x, sigmas, cfg_guidance, cond, callback_fn)
 
 
 if __name__ == "__main__":

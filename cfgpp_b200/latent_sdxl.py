@@ -10,8 +10,10 @@ forward, the CFG++ guidance mix and the scheduler update run in hand-written sm_
 no host synchronisation; with a callback the un-fused seam (`predict_noise` + `apply_step`) is used so that `z0t` /
 `zt` are materialised and may be replaced by the callback, exactly like the reference loop.
 
-Registered here: ddim_cfg++, ddim_cfg++_lightning, dpm++_2m_cfgpp (the solvers of SURVEY.md §8a). Text encoders and
-the VAE stay on the reference path (see conditioning.py).
+Registered here: ddim_cfg++, ddim_cfg++_lightning, dpm++_2m_cfgpp (the solvers of SURVEY.md §8a) and, from §8 f1,
+dpm++_2m_cfgpp_lightning (:932-952), ddim_edit_cfg++ (:954-1025, both loops on the fused step modes), euler_cfg++ and
+euler_cfg++_lightning (:757-836: native UNet behind `predict_noise`, the Euler update in torch — kdiffusion.py).
+Text encoders and the VAE stay on the reference path (see conditioning.py).
 """
 from __future__ import annotations
 
@@ -20,6 +22,7 @@ from typing import Any, Optional, Tuple
 
 import torch
 
+from . import kdiffusion as K
 from . import schedule as S
 from .conditioning import LatentPreviewDecoder, SyntheticTextEncoder
 from .config import UNetConfig, sdxl_config
@@ -85,7 +88,7 @@ class _Scheduler:
         self.final_alpha_cumprod = sch.final_alpha_cumprod
 
 
-class SDXL():
+class SDXL(K.KDiffusionMixin):
     schedule_kind = "ddim"
     quantize = True
 
@@ -251,14 +254,24 @@ class SDXL():
             sigmas = kwargs.get('sigmas', [14.6146])
             z = torch.randn(size).to(self.device)
             z = z * (sigmas[0] ** 2 + 1) ** 0.5
-        elif method in ('ddim', 'npi'):
-            raise NotImplementedError("SDXL inversion (ddim_edit*) is outside the CFG++ hot-path scope (SURVEY §8 f1)")
+        elif method == 'ddim':
+            assert src_img is not None, "src_img must be provided for inversion"
+            z = self.inversion(self.encode(src_img.to(self.dtype).to(self.device)), kwargs.get('uc'), kwargs.get('c'),
+                               kwargs.get('cfg_guidance', 0.0), add_cond_kwargs)
+        elif method == 'npi':
+            assert src_img is not None, "src_img must be provided for inversion"
+            z = self.inversion(self.encode(src_img.to(self.dtype).to(self.device)), kwargs.get('c'), kwargs.get('c'),
+                               1.0, add_cond_kwargs)
         else:
             raise NotImplementedError
         return z
 
     def reverse_process(self, *args, **kwargs):
         raise NotImplementedError
+
+    def inversion(self, z0, uc, c, cfg_guidance, add_cond_kwargs):
+        raise NotImplementedError("plain-CFG DDIM inversion is outside the CFG++ scope (SURVEY §8 f4); "
+                                  "ddim_edit_cfg++ brings its own CFG++ inversion")
 
     def sigma_to_t(self, sigma, quantize=None):
         quantize = self.quantize if quantize is None else quantize
@@ -371,6 +384,129 @@ class DPMpp2mCFGppSolver(SDXL):
         x = x * sigma0  # fp16 tensor x 0-dim fp32 -> fp16 (latent_sdxl.py:882-884)
         return self._run_trajectory(S.STEP_DPMPP2M_CFGPP, torch.float16, steps, x, null_prompt_embeds, prompt_embeds,
                                     add_cond_kwargs, callback_fn, 'zt')
+
+
+@register_solver('dpm++_2m_cfgpp_lightning')
+class DPMpp2mCFGppLightningSolver(DPMpp2mCFGppSolver, SDXLLightning):
+    def __init__(self, **kwargs):
+        SDXLLightning.__init__(self, **kwargs)
+
+    def reverse_process(self, null_prompt_embeds, prompt_embeds, cfg_guidance, add_cond_kwargs, shape=(1024, 1024),
+                        callback_fn=None, **kwargs):
+        assert cfg_guidance == 1.0, "CFG should be turned off in the lightning version"
+        return super().reverse_process(null_prompt_embeds, prompt_embeds, cfg_guidance, add_cond_kwargs, shape,
+                                       callback_fn, **kwargs)
+
+
+@register_solver('euler_cfg++')
+class EulerCFGpp(SDXL):
+    """Karras Euler (VE casted) with CFG++ on the sampling timesteps' own sigmas (latent_sdxl.py:757-808): the native
+    UNet behind `predict_noise`, the Euler update in torch (kdiffusion.py)."""
+    quantize = True
+
+    @torch.no_grad()
+    def reverse_process(self, null_prompt_embeds, prompt_embeds, cfg_guidance, add_cond_kwargs, shape=(1024, 1024),
+                        callback_fn=None, **kwargs):
+        total_sigmas = self.total_sigmas()
+        sigmas = total_sigmas[torch.round(self.scheduler.timesteps.cpu()).int()]
+        sigmas = torch.cat([sigmas, torch.tensor([0.0])])
+        zt = kwargs.get('xT')
+        if zt is None:
+            zt_dim = (1, 4, shape[1] // self.vae_scale_factor, shape[0] // self.vae_scale_factor)
+            zt = self.initialize_latent(method="random_kdiffusion", latent_dim=zt_dim, sigmas=sigmas)
+        z0t, _ = K.euler_cfgpp_loop(self, zt.to(torch.float16), sigmas, cfg_guidance,
+                                    (null_prompt_embeds, prompt_embeds, add_cond_kwargs), callback_fn)
+        return z0t
+
+
+@register_solver('euler_cfg++_lightning')
+class EulerCFGppLight(EulerCFGpp, SDXLLightning):
+    quantize = True
+
+    def __init__(self, **kwargs):
+        SDXLLightning.__init__(self, **kwargs)
+
+    def reverse_process(self, null_prompt_embeds, prompt_embeds, cfg_guidance, add_cond_kwargs, shape=(1024, 1024),
+                        callback_fn=None, **kwargs):
+        assert cfg_guidance == 1.0, "CFG should be turned off in the lightning version"
+        return super().reverse_process(null_prompt_embeds, prompt_embeds, cfg_guidance, add_cond_kwargs, shape,
+                                       callback_fn, **kwargs)
+
+
+class EditWardSwapDDIM(SDXL):
+    """Three-prompt front end of the editing solvers (prompt = [null, source, target]) — latent_sdxl.py:570-655.
+    Subclasses provide `inversion` and `reverse_process`."""
+
+    def sample(self,
+               prompt1=["", "", ""],
+               prompt2=["", "", ""],
+               cfg_guidance: float = 5.0,
+               original_size: Optional[Tuple[int, int]] = None,
+               crops_coords_top_left: Tuple[int, int] = (0, 0),
+               target_size: Optional[Tuple[int, int]] = None,
+               negative_original_size: Optional[Tuple[int, int]] = None,
+               negative_crops_coords_top_left: Tuple[int, int] = (0, 0),
+               negative_target_size: Optional[Tuple[int, int]] = None,
+               clip_skip: Optional[int] = None,
+               **kwargs):
+        height = self.default_sample_size * self.vae_scale_factor
+        width = self.default_sample_size * self.vae_scale_factor
+        original_size = original_size or (height, width)
+        target_size = target_size or (height, width)
+
+        (null_prompt_embeds, src_prompt_embeds, pool_null_embed, pool_src) = self.get_text_embed(
+            prompt1[0], prompt1[1], prompt2[0], prompt2[1], clip_skip)
+        (_, tgt_prompt_embeds, _, pool_tgt) = self.get_text_embed(prompt1[0], prompt1[2], prompt2[0], prompt2[2],
+                                                                  clip_skip)
+        proj_dim = int(pool_src.shape[-1])
+        add_time_ids = self._get_add_time_ids(original_size, crops_coords_top_left, target_size,
+                                              dtype=src_prompt_embeds.dtype, text_encoder_projection_dim=proj_dim)
+        if negative_original_size is not None and negative_target_size is not None:
+            negative_add_time_ids = self._get_add_time_ids(negative_original_size, negative_crops_coords_top_left,
+                                                           negative_target_size, dtype=src_prompt_embeds.dtype,
+                                                           text_encoder_projection_dim=proj_dim)
+        else:
+            negative_add_time_ids = add_time_ids
+        add_src, add_tgt = pool_src, pool_tgt
+        if cfg_guidance != 0.0 and cfg_guidance != 1.0:
+            add_src = torch.cat([pool_null_embed, add_src], dim=0)
+            add_tgt = torch.cat([pool_null_embed, add_tgt], dim=0)
+            add_time_ids = torch.cat([negative_add_time_ids, add_time_ids], dim=0)
+        add_src_cond_kwargs = {'text_embeds': add_src.to(self.device), 'time_ids': add_time_ids.to(self.device)}
+        add_tgt_cond_kwargs = {'text_embeds': add_tgt.to(self.device), 'time_ids': add_time_ids.to(self.device)}
+
+        zt = self.reverse_process(null_prompt_embeds, src_prompt_embeds, tgt_prompt_embeds, cfg_guidance,
+                                  add_src_cond_kwargs, add_tgt_cond_kwargs, **kwargs)
+        with torch.no_grad():
+            img = self.decode(zt)
+        img = (img / 2 + 0.5).clamp(0, 1)
+        return img.detach().cpu()
+
+
+@register_solver("ddim_edit_cfg++")
+class EditWardSwapDDIMCFGpp(EditWardSwapDDIM):
+    """CFG++ inversion under the source prompt (Tweedie with eps_uc, renoise with the guided eps), then CFG++ DDIM
+    sampling under the target prompt — latent_sdxl.py:955-1025. Both loops index the schedule through `alpha()`
+    (negative t -> final_alpha_cumprod) and carry the fp16 VAE latent, so they run as the two fused step modes the
+    SD v1.5 `ddim_inversion_cfg++` uses."""
+
+    @torch.no_grad()
+    def inversion(self, z0, uc, c, cfg_guidance, add_cond_kwargs):
+        if cfg_guidance == 0.0 or cfg_guidance == 1.0:
+            add_cond_kwargs['text_embeds'] = add_cond_kwargs['text_embeds'][-1].unsqueeze(0)
+            add_cond_kwargs['time_ids'] = add_cond_kwargs['time_ids'][-1].unsqueeze(0)
+        steps = S.ddim_inversion_cfgpp_steps(self._sch, cfg_guidance)
+        z0 = z0.clone().to(self.device)
+        return self._run_trajectory(S.STEP_DDIM_INV_CFGPP, z0.dtype, steps, z0, uc, c, add_cond_kwargs, None, 'zt')
+
+    def reverse_process(self, null_prompt_embeds, src_prompt_embeds, tgt_prompt_embed, cfg_guidance,
+                        add_src_cond_kwargs, add_tgt_cond_kwargs, callback_fn=None, **kwargs):
+        zt = self.initialize_latent(method='ddim', src_img=kwargs.get('src_img', None), uc=null_prompt_embeds,
+                                    c=src_prompt_embeds, cfg_guidance=cfg_guidance,
+                                    add_cond_kwargs=add_src_cond_kwargs)
+        steps = S.ddim_cfgpp_steps(self._sch, cfg_guidance, sdxl_indexing=False)
+        return self._run_trajectory(S.STEP_DDIM_CFGPP, zt.dtype, steps, zt, null_prompt_embeds, tgt_prompt_embed,
+                                    add_tgt_cond_kwargs, callback_fn, 'z0t')
 
 
 if __name__ == "__main__":

@@ -177,3 +177,152 @@ def sdxl_dpmpp_2m_cfgpp(unet, tb: ScheduleTables, noise, uc, c, cfg_guidance: fl
             kw = callback_fn(i, new_t, {"z0t": denoised.detach(), "zt": x.detach(), "decode": None})
             denoised, x = kw["z0t"], kw["zt"]
     return x
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the VE-cast ("k-diffusion") CFG++ samplers and the CFG++ editing loops.
+#   helpers                       latent_diffusion.py:30-37 (ancestral step), :211-241 (timestep / to_d / x->denoised)
+#   SD v1.5 euler_cfg++           latent_diffusion.py:682-724      euler_a_cfg++   :727-768
+#   SD v1.5 dpm++_2s_a_cfg++      latent_diffusion.py:771-827      dpm++_2m_cfg++  :830-879
+#   SD v1.5 ddim_edit_cfg++       latent_diffusion.py:959-1010
+#   SDXL    euler_cfg++           latent_sdxl.py:757-808           ddim_edit_cfg++ :954-1025
+# Same conventions as above: conditioning tensors and the N(0,1) draw are passed in; CPU 0-dim sigmas.
+# ------------------------------------------------------------------------------------------------------------------
+
+def ancestral_step(sigma_from, sigma_to, eta=1.0):
+    """latent_diffusion.py:30-37."""
+    if not eta:
+        return sigma_to, 0.0
+    sigma_up = min(sigma_to, eta * (sigma_to ** 2 * (sigma_from ** 2 - sigma_to ** 2) / sigma_from ** 2) ** 0.5)
+    sigma_down = (sigma_to ** 2 - sigma_up ** 2) ** 0.5
+    return sigma_down, sigma_up
+
+
+def kd_timestep(tb: ScheduleTables, sigma: torch.Tensor) -> torch.Tensor:
+    """StableDiffusion.timestep / SDXL.timestep (latent_diffusion.py:211-214): nearest training level in log-sigma."""
+    dists = sigma.log() - tb.log_sigmas[:, None]
+    return dists.abs().argmin(dim=0).view(sigma.shape)
+
+
+def kd_denoised(unet, x, sigma, t, uc, c, cfg_guidance, add_cond_kwargs=None):
+    """kdiffusion_x_to_denoised (latent_diffusion.py:232-241) / kdiffusion_zt_to_denoised (latent_sdxl.py:357-363)."""
+    xc = x / (sigma ** 2 + 1) ** 0.5
+    noise_uc, noise_c = predict_noise(unet, xc, t, uc, c, add_cond_kwargs)
+    noise_pred = noise_uc + cfg_guidance * (noise_c - noise_uc)
+    return x - noise_pred * sigma, x - noise_uc * sigma
+
+
+def karras_sigmas(tb: ScheduleTables):
+    from .schedule import get_sigmas_karras
+    total_sigmas = (1 - tb.total_alphas).sqrt() / tb.total_alphas.sqrt()
+    return get_sigmas_karras(len(tb.timesteps), total_sigmas.min(), total_sigmas.max(), rho=7.0)
+
+
+@torch.no_grad()
+def kd_euler_cfgpp(unet, tb, x, sigmas, uc, c, cfg_guidance, add_cond_kwargs=None, ancestral=False):
+    """The loop body shared by euler_cfg++ (latent_diffusion.py:701-711, latent_sdxl.py:787-799) and euler_a_cfg++
+    (latent_diffusion.py:745-755). x is the scaled fp16 start state. Returns (last denoised, x)."""
+    denoised = None
+    for i in range(len(sigmas) - 1):
+        sigma = sigmas[i]
+        t = kd_timestep(tb, sigma).to(x.device)
+        denoised, uncond_denoised = kd_denoised(unet, x, sigma, t, uc, c, cfg_guidance, add_cond_kwargs)
+        d = (x - uncond_denoised) / sigma.item()
+        if ancestral:
+            sigma_down, sigma_up = ancestral_step(sigmas[i], sigmas[i + 1])
+            x = denoised + d * sigma_down
+            if sigmas[i + 1] > 0:
+                x = x + torch.randn_like(x) * sigma_up
+        else:
+            x = denoised + d * sigmas[i + 1]
+    return denoised, x
+
+
+@torch.no_grad()
+def kd_dpmpp_2s_a_cfgpp(unet, tb, x, sigmas, uc, c, cfg_guidance):
+    """latent_diffusion.py:786-817."""
+    t_fn = lambda sigma: sigma.log().neg()  # noqa: E731
+    sigma_fn = lambda t: t.neg().exp()      # noqa: E731
+    denoised = None
+    for i in range(len(sigmas) - 1):
+        sigma = sigmas[i]
+        new_t = kd_timestep(tb, sigma).to(x.device)
+        denoised, uncond_denoised = kd_denoised(unet, x, sigma, new_t, uc, c, cfg_guidance)
+        sigma_down, sigma_up = ancestral_step(sigmas[i], sigmas[i + 1])
+        if sigma_down == 0:
+            d = (x - uncond_denoised) / sigmas[i].item()
+            x = denoised + d * sigma_down
+        else:
+            t, t_next = t_fn(sigmas[i]), t_fn(sigma_down)
+            r = 1 / 2
+            h = t_next - t
+            s = t + r * h
+            x_2 = (sigma_fn(s) / sigma_fn(t)) * x - (-h * r).expm1() * uncond_denoised
+            sigma_s = sigma_fn(s)
+            t_2 = kd_timestep(tb, sigma_s).to(x.device)
+            denoised_2, uncond_denoised_2 = kd_denoised(unet, x_2, sigma_s, t_2, uc, c, cfg_guidance)
+            x = denoised_2 - torch.exp(-h) * uncond_denoised_2 + (sigma_fn(t_next) / sigma_fn(t)) * x
+        if sigmas[i + 1] > 0:
+            x = x + torch.randn_like(x) * sigma_up
+    return denoised, x
+
+
+@torch.no_grad()
+def kd_dpmpp_2m_cfgpp_sd15(unet, tb, x, sigmas, uc, c, cfg_guidance):
+    """latent_diffusion.py:848-866 — second-order term on (denoised - old_denoised) (the SDXL file uses
+    uncond_denoised there, see sdxl_dpmpp_2m_cfgpp above)."""
+    t_fn = lambda sigma: sigma.log().neg()  # noqa: E731
+    old_denoised = None
+    denoised = None
+    for i in range(len(sigmas) - 1):
+        sigma = sigmas[i]
+        new_t = kd_timestep(tb, sigma).to(x.device)
+        denoised, uncond_denoised = kd_denoised(unet, x, sigma, new_t, uc, c, cfg_guidance)
+        t, t_next = t_fn(sigmas[i]), t_fn(sigmas[i + 1])
+        h = t_next - t
+        if old_denoised is None or sigmas[i + 1] == 0:
+            x = denoised + (x - uncond_denoised) / sigmas[i].item() * sigmas[i + 1]
+        else:
+            h_last = t - t_fn(sigmas[i - 1])
+            r = h_last / h
+            extra1 = -torch.exp(-h) * uncond_denoised - (-h).expm1() * (denoised - old_denoised) / (2 * r)
+            extra2 = torch.exp(-h) * x
+            x = denoised + extra1 + extra2
+        old_denoised = uncond_denoised
+    return denoised, x
+
+
+def sdxl_euler_sigmas(tb: ScheduleTables):
+    """latent_sdxl.py:773-778: the sampling timesteps' own sigmas (not Karras) plus a trailing 0."""
+    total_sigmas = (1 - tb.total_alphas).sqrt() / tb.total_alphas.sqrt()
+    sigmas = total_sigmas[torch.round(tb.timesteps.cpu()).int()]
+    return torch.cat([sigmas, torch.tensor([0.0])])
+
+
+def kd_start_state(noise, sigmas):
+    """initialize_latent('random_kdiffusion') + the fp16 cast of the samplers (latent_diffusion.py:203-207, :695-697)."""
+    return (noise * (sigmas[0] ** 2 + 1) ** 0.5).to(torch.float16)
+
+
+@torch.no_grad()
+def ddim_edit_cfgpp(unet, tb, z0_src, uc, c_src, c_tgt, cfg_guidance, add_src=None, add_tgt=None):
+    """ddim_edit_cfg++: CFG++ inversion under the source prompt, CFG++ DDIM under the target prompt, both through
+    alpha() (latent_diffusion.py:959-1010 with :888-910; latent_sdxl.py:955-1025). fp16 state throughout."""
+    if add_src is not None and (cfg_guidance == 0.0 or cfg_guidance == 1.0):
+        add_src = {k: v[-1].unsqueeze(0) for k, v in add_src.items()}
+    zt = z0_src.clone()
+    for t in reversed(tb.timesteps):
+        at, at_prev = _alpha_sd15(tb, t), _alpha_sd15(tb, t - tb.skip)
+        noise_uc, noise_c = predict_noise(unet, zt, t.to(zt.device), uc, c_src, add_src)
+        noise_pred = noise_uc + cfg_guidance * (noise_c - noise_uc)
+        z0t = (zt - (1 - at_prev).sqrt() * noise_uc) / at_prev.sqrt()
+        zt = at.sqrt() * z0t + (1 - at).sqrt() * noise_pred
+    zT = zt
+    z0t = None
+    for t in tb.timesteps:
+        at, at_next = _alpha_sd15(tb, t), _alpha_sd15(tb, t - tb.skip)
+        noise_uc, noise_c = predict_noise(unet, zt, t.to(zt.device), uc, c_tgt, add_tgt)
+        noise_pred = noise_uc + cfg_guidance * (noise_c - noise_uc)
+        z0t = (zt - (1 - at).sqrt() * noise_pred) / at.sqrt()
+        zt = at_next.sqrt() * z0t + (1 - at_next).sqrt() * noise_uc
+    return zT, z0t

@@ -16,6 +16,9 @@ def test_registries_mirror_reference_names_and_errors():
     from cfgpp_b200 import latent_sdxl as LX
     assert {"ddim_cfg++", "ddim_inversion_cfg++"} <= set(LD.__SOLVER__)
     assert {"ddim_cfg++", "ddim_cfg++_lightning", "dpm++_2m_cfgpp"} <= set(LX.__SOLVER__)
+    # the rest of the CFG++ --method surface
+    assert {"euler_cfg++", "euler_a_cfg++", "dpm++_2s_a_cfg++", "dpm++_2m_cfg++", "ddim_edit_cfg++"} <= set(LD.__SOLVER__)
+    assert {"euler_cfg++", "euler_cfg++_lightning", "dpm++_2m_cfgpp_lightning", "ddim_edit_cfg++"} <= set(LX.__SOLVER__)
     with pytest.raises(ValueError, match="does not exist"):
         LX.get_solver("no_such_solver")
     with pytest.raises(ValueError, match="already registered"):

@@ -238,3 +238,83 @@ def test_solver_api_end_to_end_and_callback_path():
     im2 = inv.sample(src_img=src, prompt=["", "a dog"], cfg_guidance=0.6)
     assert im2.shape == (1, 3, 256, 256) and torch.isfinite(im2).all()
     assert a.shape == img.shape
+
+
+# ---- the VE-cast CFG++ samplers and the CFG++ editing loops on the native UNet seam ----------
+
+@pytest.mark.parametrize("method", ["euler_cfg++", "euler_a_cfg++", "dpm++_2s_a_cfg++", "dpm++_2m_cfg++"])
+def test_sd15_kdiffusion_cfgpp_solvers_vs_oracle(method):
+    """Free-running trajectories (NFE=6, Karras sigmas, fp16 state): product solver (native UNet behind predict_noise)
+    vs the oracle loop on the fp16-autocast oracle UNet, same start state, same CUDA noise stream for the ancestral
+    variants. Stated tolerance: rel-L2 of the final state / Tweedie estimate <= 3e-2 (as for the DDIM trajectories)."""
+    from cfgpp_b200 import latent_diffusion as LD
+    from oracle import samplers as OSm, schedule as OS
+    cfg, sd, net, ref = build_pair("tiny_sd15", dev)
+    net.close()
+    nfe, lam, hw = 6, 0.6, 32
+    z, uc, c, _ = make_inputs(cfg, 1, hw, dev)
+    solver = LD.get_solver(method, solver_config=SimpleNamespace(num_sampling=nfe), device=dev, unet_config=cfg,
+                           state_dict=sd)
+    tb = OS.make_tables(nfe)
+    sigmas = solver.karras_sigmas()
+    assert torch.equal(sigmas, OSm.karras_sigmas(tb))
+    x0 = OSm.kd_start_state(z, sigmas)
+    oracle_loop = {"euler_cfg++": lambda: OSm.kd_euler_cfgpp(ref, tb, x0.clone(), sigmas, uc, c, lam),
+                   "euler_a_cfg++": lambda: OSm.kd_euler_cfgpp(ref, tb, x0.clone(), sigmas, uc, c, lam, ancestral=True),
+                   "dpm++_2s_a_cfg++": lambda: OSm.kd_dpmpp_2s_a_cfgpp(ref, tb, x0.clone(), sigmas, uc, c, lam),
+                   "dpm++_2m_cfg++": lambda: OSm.kd_dpmpp_2m_cfgpp_sd15(ref, tb, x0.clone(), sigmas, uc, c, lam)}[method]
+    torch.manual_seed(123)
+    d_ref, x_ref = oracle_loop()
+    torch.manual_seed(123)
+    d, x = solver.reverse_process(uc, c, lam, x0.clone())
+    assert x.dtype == torch.float16 and d.dtype == torch.float16
+    e_x, e_d = rel_l2(x, x_ref), rel_l2(d, d_ref)
+    print(f"{method}: rel-L2 final x {e_x:.3e}, last denoised {e_d:.3e}")
+    assert e_x <= 3e-2 and e_d <= 3e-2
+    img = solver.sample(cfg_guidance=lam, prompt=["", "a dog"])
+    assert img.shape == (1, 3, 8 * cfg.sample_size, 8 * cfg.sample_size) and torch.isfinite(img).all()
+
+
+def test_sdxl_euler_and_edit_cfgpp_vs_oracle():
+    from cfgpp_b200 import latent_sdxl as LX
+    from oracle import samplers as OSm, schedule as OS
+    cfg, sd, net, ref = build_pair("tiny_sdxl", dev)
+    net.close()
+    nfe, lam, hw = 5, 0.6, 32
+    z, uc, c, add = make_inputs(cfg, 1, hw, dev)
+    g = torch.Generator().manual_seed(5)
+    c_tgt = torch.randn(1, 77, cfg.cross_attention_dim, generator=g).half().to(dev)
+    add_tgt = {"text_embeds": torch.randn(2, cfg.pooled_dim, generator=g).half().to(dev), "time_ids": add["time_ids"]}
+    tb = OS.make_tables(nfe)
+    kw = dict(solver_config=SimpleNamespace(num_sampling=nfe), device=dev, unet_config=cfg, state_dict=sd)
+    # euler_cfg++ on the sampling timesteps' sigmas
+    eul = LX.get_solver("euler_cfg++", **kw)
+    sigmas = OSm.sdxl_euler_sigmas(tb)
+    x0 = OSm.kd_start_state(z, sigmas)
+    z0_ref, _ = OSm.kd_euler_cfgpp(ref, tb, x0.clone(), sigmas, uc, c, lam, add)
+    z0 = eul.reverse_process(uc, c, lam, add, shape=(8 * hw, 8 * hw), xT=x0.clone())
+    e = rel_l2(z0, z0_ref)
+    print(f"sdxl euler_cfg++: rel-L2 last z0t {e:.3e}")
+    assert z0.dtype == torch.float16 and e <= 3e-2
+    # ddim_edit_cfg++: CFG++ inversion under the source prompt, CFG++ DDIM under the target prompt (fused step modes)
+    ed = LX.get_solver("ddim_edit_cfg++", **kw)
+    z0_src = (0.4 * z).half()
+    ed.encode = lambda img: z0_src  # the VAE is outside the path: inject its latent
+    zT_ref, z0t_ref = OSm.ddim_edit_cfgpp(ref, tb, z0_src, uc, c, c_tgt, lam, dict(add), dict(add_tgt))
+    zT = ed.inversion(z0_src, uc, c, lam, dict(add))
+    assert zT.dtype == torch.float16 and rel_l2(zT, zT_ref) <= 3e-2
+    z0t = ed.reverse_process(uc, c, c_tgt, lam, dict(add), dict(add_tgt), src_img=torch.zeros(1, 3, 8 * hw, 8 * hw))
+    e = rel_l2(z0t, z0t_ref)
+    print(f"sdxl ddim_edit_cfg++: rel-L2 zT {rel_l2(zT, zT_ref):.3e}, edited z0t {e:.3e}")
+    assert z0t.dtype == torch.float16 and e <= 3e-2
+    # Lightning flavours: registry + the guidance assertion
+    with pytest.warns(UserWarning):
+        lt = LX.get_solver("dpm++_2m_cfgpp_lightning", solver_config=SimpleNamespace(num_sampling=4), device=dev,
+                           unet_config=cfg)
+    with pytest.raises(AssertionError, match="CFG should be turned off"):
+        lt.reverse_process(uc, c, 0.6, add)
+    with pytest.warns(UserWarning):
+        le = LX.get_solver("euler_cfg++_lightning", solver_config=SimpleNamespace(num_sampling=4), device=dev,
+                           unet_config=cfg)
+    out = le.reverse_process(uc, c, 1.0, {k: v[-1:].clone() for k, v in add.items()}, shape=(8 * hw, 8 * hw))
+    assert out.shape == (1, 4, hw, hw) and torch.isfinite(out).all()
