@@ -208,9 +208,11 @@ CFGPP_DEVICE void cfgpp_update(int mode, const StepCoef& k, float eu, float ec, 
   // noise_pred = eps_uc + lambda * (eps_c - eps_uc)   (three fp16 tensor ops)
   const float np = rh(__fadd_rn(eu, rh(__fmul_rn(k.lambda, rh(__fsub_rn(ec, eu))))));
   new_old = 0.f;
-  if (mode == STEP_DDIM_CFGPP || mode == STEP_DDIM_INV_CFGPP) {
-    const float e_tw = (mode == STEP_DDIM_CFGPP) ? np : eu;  // Tweedie uses guided eps (sampling) / eps_uc (inversion)
-    const float e_rn = (mode == STEP_DDIM_CFGPP) ? eu : np;  // renoise uses eps_uc (sampling) / guided eps (inversion)
+  if (mode == STEP_DDIM_CFGPP || mode == STEP_DDIM_INV_CFGPP || mode == STEP_DDIM_CFG) {
+    // Tweedie: guided eps (CFG++ sampling, plain CFG) / eps_uc (CFG++ inversion);
+    // renoise: eps_uc (CFG++ sampling) / guided eps (CFG++ inversion, plain CFG in both directions)
+    const float e_tw = (mode == STEP_DDIM_INV_CFGPP) ? eu : np;
+    const float e_rn = (mode == STEP_DDIM_CFGPP) ? eu : np;
     const float a = rh(__fmul_rn(k.c0, e_tw));
     z0t = rs<kHalfState>(__fdiv_rn(rs<kHalfState>(__fsub_rn(z, a)), k.c1));
     const float b = rh(__fmul_rn(k.c3, e_rn));

@@ -40,6 +40,8 @@ enum StepMode : int {
   STEP_DDIM_CFGPP = 1,  // latent_diffusion.py:660-666, latent_sdxl.py:738-744 (fp32 state)
   STEP_DDIM_INV_CFGPP = 2,  // latent_diffusion.py:904-908 (fp32 state)
   STEP_DPMPP2M_CFGPP = 3,   // latent_sdxl.py:902-919 (fp16 state, keeps old_denoised)
+  STEP_DDIM_CFG = 4,        // plain-CFG DDIM step / inversion step: Tweedie AND renoise with the guided eps
+                            // (latent_diffusion.py:283-287, :176-177; latent_sdxl.py:451-455, :321-322)
 };
 
 struct StepCoef {  // per-step scalars, computed on the host in fp32 exactly as the reference does

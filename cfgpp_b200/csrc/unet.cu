@@ -995,7 +995,7 @@ std::vector<Unet::ProfEntry> Unet::profile_forward(const void* z, int z_dtype, f
 // ------------------------------------------------------------------------------------------------------------
 void Unet::set_schedule(int method, int state_dtype, const cfgpp_step_state* steps, int nsteps, cudaStream_t stream) {
   CFGPP_REQUIRE(prepared_, "call cfgpp_prepare first");
-  CFGPP_REQUIRE(method >= CFGPP_STEP_DDIM_CFGPP && method <= CFGPP_STEP_DPMPP2M_CFGPP, "unknown method");
+  CFGPP_REQUIRE(method >= CFGPP_STEP_DDIM_CFGPP && method <= CFGPP_STEP_DDIM_CFG, "unknown method");
   CFGPP_REQUIRE(nsteps >= 1 && nsteps <= 1024, "nsteps must be 1..1024");
   static_assert(sizeof(cfgpp_step_state) == sizeof(StepState), "ABI struct mismatch");
   static_assert(sizeof(cfgpp_step_coef) == sizeof(StepCoef), "ABI struct mismatch");

@@ -1,4 +1,5 @@
-"""k-diffusion (VE-cast) CFG++ samplers on the native UNet seam  — SURVEY §8 f1.
+"""k-diffusion (VE-cast) samplers on the native UNet seam — CFG++ variants and, with `cfgpp=False`, the
+plain-CFG baselines they are compared against (§8 f4: latent_diffusion.py:302-503, latent_sdxl.py:469-517).
 
 The reference expresses `euler_cfg++`, `euler_a_cfg++`, `dpm++_2s_a_cfg++` and `dpm++_2m_cfg++` through one helper,
 `kdiffusion_x_to_denoised` (latent_diffusion.py:232-241; SDXL twin `kdiffusion_zt_to_denoised`, latent_sdxl.py:357-363):
@@ -83,17 +84,17 @@ def _callback(callback_fn: Optional[Callable], i, t, z0t, zt, decode):
 
 @torch.no_grad()
 def euler_cfgpp_loop(solver: KDiffusionMixin, x, sigmas, cfg_guidance, cond, callback_fn=None,
-                     ancestral: bool = False, adopt_callback: bool = True):
+                     ancestral: bool = False, adopt_callback: bool = True, cfgpp: bool = True):
     """Euler (optionally ancestral) CFG++: x' = D_guided(x) + sigma' * (x - D_uncond(x)) / sigma  [+ sigma_up * N(0,1)].
     latent_diffusion.py:699-719 (euler_cfg++), :744-762 (euler_a_cfg++), latent_sdxl.py:787-808 (SDXL euler_cfg++).
     Returns (last denoised, x). `adopt_callback`: the ancestral variant of the reference ignores what the callback
-    returns (:757-762)."""
+    returns (:757-762). `cfgpp=False`: plain CFG, the derivative uses the guided estimate (:326-330, :372-379)."""
     denoised = None
     for i in range(len(sigmas) - 1):
         sigma = sigmas[i]
         t = solver.timestep(sigma).to(solver.device)
         denoised, uncond_denoised = solver._k_denoise(x, sigma, t, cfg_guidance, cond)
-        d = solver.to_d(x, sigma, uncond_denoised)
+        d = solver.to_d(x, sigma, uncond_denoised if cfgpp else denoised)
         if ancestral:
             sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1])
             x = denoised + d * sigma_down
@@ -108,9 +109,11 @@ def euler_cfgpp_loop(solver: KDiffusionMixin, x, sigmas, cfg_guidance, cond, cal
 
 
 @torch.no_grad()
-def dpmpp_2s_a_cfgpp_loop(solver: KDiffusionMixin, x, sigmas, cfg_guidance, cond, callback_fn=None):
+def dpmpp_2s_a_cfgpp_loop(solver: KDiffusionMixin, x, sigmas, cfg_guidance, cond, callback_fn=None,
+                          cfgpp: bool = True):
     """DPM-Solver++(2S) ancestral, CFG++: both the midpoint and the final update extrapolate with the unconditional
-    Tweedie estimate — latent_diffusion.py:782-825 (two UNet calls per step)."""
+    Tweedie estimate — latent_diffusion.py:782-825 (two UNet calls per step). `cfgpp=False`: the plain-CFG original
+    (:408-437), guided estimate everywhere and the standard final update."""
     t_fn = lambda s: s.log().neg()      # noqa: E731
     sigma_fn = lambda t: t.neg().exp()  # noqa: E731
     denoised = None
@@ -119,18 +122,22 @@ def dpmpp_2s_a_cfgpp_loop(solver: KDiffusionMixin, x, sigmas, cfg_guidance, cond
         new_t = solver.timestep(sigma).to(solver.device)
         denoised, uncond_denoised = solver._k_denoise(x, sigma, new_t, cfg_guidance, cond)
         sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1])
+        extrap = uncond_denoised if cfgpp else denoised
         if sigma_down == 0:
-            x = denoised + solver.to_d(x, sigmas[i], uncond_denoised) * sigma_down
+            x = denoised + solver.to_d(x, sigmas[i], extrap) * sigma_down
         else:
             t, t_next = t_fn(sigmas[i]), t_fn(sigma_down)
             r = 1 / 2
             h = t_next - t
             s = t + r * h
-            x_2 = (sigma_fn(s) / sigma_fn(t)) * x - (-h * r).expm1() * uncond_denoised
+            x_2 = (sigma_fn(s) / sigma_fn(t)) * x - (-h * r).expm1() * extrap
             sigma_s = sigma_fn(s)
             t_2 = solver.timestep(sigma_s).to(solver.device)
             denoised_2, uncond_denoised_2 = solver._k_denoise(x_2, sigma_s, t_2, cfg_guidance, cond)
-            x = denoised_2 - torch.exp(-h) * uncond_denoised_2 + (sigma_fn(t_next) / sigma_fn(t)) * x
+            if cfgpp:
+                x = denoised_2 - torch.exp(-h) * uncond_denoised_2 + (sigma_fn(t_next) / sigma_fn(t)) * x
+            else:
+                x = (sigma_fn(t_next) / sigma_fn(t)) * x - (-h).expm1() * denoised_2
         if sigmas[i + 1] > 0:
             x = x + torch.randn_like(x) * sigma_up
         denoised, x = _callback(callback_fn, i, new_t, denoised, x, solver.decode)
@@ -138,10 +145,12 @@ def dpmpp_2s_a_cfgpp_loop(solver: KDiffusionMixin, x, sigmas, cfg_guidance, cond
 
 
 @torch.no_grad()
-def dpmpp_2m_cfgpp_karras_loop(solver: KDiffusionMixin, x, sigmas, cfg_guidance, cond, callback_fn=None):
+def dpmpp_2m_cfgpp_karras_loop(solver: KDiffusionMixin, x, sigmas, cfg_guidance, cond, callback_fn=None,
+                               cfgpp: bool = True):
     """SD v1.5 `dpm++_2m_cfg++` (latent_diffusion.py:847-877). NOTE the reference's two files differ: this variant's
     second-order term uses (denoised - old_denoised) with the GUIDED estimate, SDXL's `dpm++_2m_cfgpp` uses the
-    unconditional one (latent_sdxl.py:916; that one runs on the fused step kernel)."""
+    unconditional one (latent_sdxl.py:916; that one runs on the fused step kernel). `cfgpp=False`: plain `dpm++_2m`
+    (:470-487), guided estimate everywhere."""
     t_fn = lambda s: s.log().neg()  # noqa: E731
     old_denoised = None
     denoised = None
@@ -151,14 +160,15 @@ def dpmpp_2m_cfgpp_karras_loop(solver: KDiffusionMixin, x, sigmas, cfg_guidance,
         denoised, uncond_denoised = solver._k_denoise(x, sigma, new_t, cfg_guidance, cond)
         t, t_next = t_fn(sigmas[i]), t_fn(sigmas[i + 1])
         h = t_next - t
+        extrap = uncond_denoised if cfgpp else denoised
         if old_denoised is None or sigmas[i + 1] == 0:
-            x = denoised + solver.to_d(x, sigmas[i], uncond_denoised) * sigmas[i + 1]
+            x = denoised + solver.to_d(x, sigmas[i], extrap) * sigmas[i + 1]
         else:
             h_last = t - t_fn(sigmas[i - 1])
             r = h_last / h
-            extra1 = -torch.exp(-h) * uncond_denoised - (-h).expm1() * (denoised - old_denoised) / (2 * r)
+            extra1 = -torch.exp(-h) * extrap - (-h).expm1() * (denoised - old_denoised) / (2 * r)
             extra2 = torch.exp(-h) * x
             x = denoised + extra1 + extra2
-        old_denoised = uncond_denoised
+        old_denoised = extrap
         denoised, x = _callback(callback_fn, i, new_t, denoised, x, solver.decode)
     return denoised, x

@@ -126,7 +126,11 @@ class StableDiffusion(K.KDiffusionMixin):
 
     @torch.no_grad()
     def inversion(self, z0: torch.Tensor, uc: torch.Tensor, c: torch.Tensor, cfg_guidance: float = 1.0):
-        raise NotImplementedError("plain-CFG DDIM inversion is outside the CFG++ hot-path scope (SURVEY §8 f4)")
+        """Plain-CFG DDIM inversion (latent_diffusion.py:160-182): Tweedie and renoise both with the guided eps. Same
+        scalars as the CFG++ inversion; the fused step kernel's STEP_DDIM_CFG mode picks the eps."""
+        steps = S.ddim_inversion_cfgpp_steps(self._sch, cfg_guidance)
+        _, zt = self._run(S.STEP_DDIM_CFG, steps, z0.clone().to(self.device), uc, c)
+        return zt
 
     def initialize_latent(self, method: str = 'random', src_img: Optional[torch.Tensor] = None, **kwargs):
         if method == 'ddim':
@@ -146,6 +150,57 @@ class StableDiffusion(K.KDiffusionMixin):
         else:
             raise NotImplementedError
         return z
+
+
+###########################################
+# Base version (plain CFG — the baselines the paper compares against)
+###########################################
+
+@register_solver("ddim")
+class BaseDDIM(StableDiffusion):
+    """Basic DDIM solver for SD with plain CFG (latent_diffusion.py:247-299), fused trajectory."""
+
+    def reverse_process(self, uc, c, cfg_guidance, zt, callback_fn=None):
+        steps = S.ddim_cfgpp_steps(self._sch, cfg_guidance, sdxl_indexing=False)
+        z0t, _ = self._run(S.STEP_DDIM_CFG, steps, zt, uc, c, callback_fn)
+        return z0t
+
+    def sample(self, cfg_guidance=7.5, prompt=["", ""], callback_fn=None, **kwargs):
+        uc, c = self.get_text_embed(null_prompt=prompt[0], prompt=prompt[1])
+        zt = kwargs.get('zT')
+        if zt is None:
+            zt = self.initialize_latent()
+        z0t = self.reverse_process(uc, c, cfg_guidance, zt, callback_fn)
+        img = self.decode(z0t)
+        img = (img / 2 + 0.5).clamp(0, 1)
+        return img.detach().cpu()
+
+
+@register_solver("ddim_inversion")
+class InversionDDIM(BaseDDIM):
+    """Reconstruction / editing after plain-CFG inversion (latent_diffusion.py:506-558)."""
+
+    def sample(self, src_img, cfg_guidance=7.5, prompt=["", "", ""], callback_fn=None, **kwargs):
+        uc, c = self.get_text_embed(null_prompt=prompt[0], prompt=prompt[1])
+        zt = self.initialize_latent(method='ddim', src_img=src_img, uc=uc, c=c, cfg_guidance=cfg_guidance)
+        z0t = self.reverse_process(uc, c, cfg_guidance, zt, callback_fn)
+        img = self.decode(z0t)
+        img = (img / 2 + 0.5).clamp(0, 1)
+        return img.detach().cpu()
+
+
+@register_solver("ddim_edit")
+class EditWordSwapDDIM(InversionDDIM):
+    """Editing via WordSwap after plain-CFG inversion (latent_diffusion.py:561-612)."""
+
+    def sample(self, src_img, cfg_guidance=7.5, prompt=["", "", ""], callback_fn=None, **kwargs):
+        uc, src_c = self.get_text_embed(null_prompt=prompt[0], prompt=prompt[1])
+        _, tgt_c = self.get_text_embed(null_prompt=prompt[0], prompt=prompt[2])
+        zt = self.initialize_latent(method='ddim', src_img=src_img, uc=uc, c=src_c, cfg_guidance=cfg_guidance)
+        z0t = self.reverse_process(uc, tgt_c, cfg_guidance, zt, callback_fn)
+        img = self.decode(z0t)
+        img = (img / 2 + 0.5).clamp(0, 1)
+        return img.detach().cpu()
 
 
 ###########################################
@@ -264,6 +319,39 @@ class DPMpp2mCFGppSolver(_KarrasCFGpp):
 
     def _loop(self, x, sigmas, cfg_guidance, cond, callback_fn):
         return K.dpmpp_2m_cfgpp_karras_loop(self, x, sigmas, cfg_guidance, cond, callback_fn)
+
+
+@register_solver("euler")
+class EulerCFGSolver(_KarrasCFGpp):
+    """Karras Euler (VE casted), plain CFG (latent_diffusion.py:302-346)."""
+    def _loop(self, x, sigmas, cfg_guidance, cond, callback_fn):
+        return K.euler_cfgpp_loop(self, x, sigmas, cfg_guidance, cond, callback_fn, adopt_callback=False, cfgpp=False)
+
+
+@register_solver("euler_a")
+class EulerAncestralCFGSolver(_KarrasCFGpp):
+    """Karras Euler + ancestral sampling, plain CFG (latent_diffusion.py:349-390)."""
+    def _loop(self, x, sigmas, cfg_guidance, cond, callback_fn):
+        return K.euler_cfgpp_loop(self, x, sigmas, cfg_guidance, cond, callback_fn, ancestral=True,
+                                  adopt_callback=False, cfgpp=False)
+
+
+@register_solver("dpm++_2s_a")
+class DPMpp2sAncestralCFGSolver(_KarrasCFGpp):
+    """DPM-Solver++(2S) ancestral, plain CFG (latent_diffusion.py:393-451)."""
+    decode_state = True
+
+    def _loop(self, x, sigmas, cfg_guidance, cond, callback_fn):
+        return K.dpmpp_2s_a_cfgpp_loop(self, x, sigmas, cfg_guidance, cond, callback_fn, cfgpp=False)
+
+
+@register_solver("dpm++_2m")
+class DPMpp2mCFGSolver(_KarrasCFGpp):
+    """DPM-Solver++(2M), plain CFG (latent_diffusion.py:454-503)."""
+    decode_state = True
+
+    def _loop(self, x, sigmas, cfg_guidance, cond, callback_fn):
+        return K.dpmpp_2m_cfgpp_karras_loop(self, x, sigmas, cfg_guidance, cond, callback_fn, cfgpp=False)
 
 
 if __name__ == "__main__":

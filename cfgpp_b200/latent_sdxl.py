@@ -269,9 +269,16 @@ class SDXL(K.KDiffusionMixin):
     def reverse_process(self, *args, **kwargs):
         raise NotImplementedError
 
+    @torch.no_grad()
     def inversion(self, z0, uc, c, cfg_guidance, add_cond_kwargs):
-        raise NotImplementedError("plain-CFG DDIM inversion is outside the CFG++ scope (SURVEY §8 f4); "
-                                  "ddim_edit_cfg++ brings its own CFG++ inversion")
+        """Plain-CFG DDIM inversion (latent_sdxl.py:301-324): Tweedie and renoise both with the guided eps; fused
+        trajectory on the STEP_DDIM_CFG mode with the fp16 VAE latent as state."""
+        if cfg_guidance == 0.0 or cfg_guidance == 1.0:
+            add_cond_kwargs['text_embeds'] = add_cond_kwargs['text_embeds'][-1].unsqueeze(0)
+            add_cond_kwargs['time_ids'] = add_cond_kwargs['time_ids'][-1].unsqueeze(0)
+        steps = S.ddim_inversion_cfgpp_steps(self._sch, cfg_guidance)
+        z0 = z0.clone().to(self.device)
+        return self._run_trajectory(S.STEP_DDIM_CFG, z0.dtype, steps, z0, uc, c, add_cond_kwargs, None, 'zt')
 
     def sigma_to_t(self, sigma, quantize=None):
         quantize = self.quantize if quantize is None else quantize
@@ -317,6 +324,72 @@ class SDXLLightning(SDXL):
         if key.startswith("synthetic"):
             warnings.warn(f"Lightning checkpoint '{light_model_ckpt}' not found; using seeded synthetic UNet weights")
         SDXL.__init__(self, solver_config, model_key=key, dtype=dtype, device=device, **kwargs)
+
+
+###########################################
+# Base version (plain CFG — the baselines the paper compares against)
+###########################################
+
+@register_solver('ddim')
+class BaseDDIM(SDXL):
+    """latent_sdxl.py:425-467: fp32 state, fused trajectory, renoise with the guided eps."""
+    step_mode = S.STEP_DDIM_CFG
+
+    def reverse_process(self, null_prompt_embeds, prompt_embeds, cfg_guidance, add_cond_kwargs, shape=(1024, 1024),
+                        callback_fn=None, **kwargs):
+        b = null_prompt_embeds.shape[0]
+        zt = kwargs.get('zT')
+        if zt is None:
+            zt = self.initialize_latent(size=(b, 4, shape[1] // self.vae_scale_factor, shape[0] // self.vae_scale_factor))
+        steps = S.ddim_cfgpp_steps(self._sch, cfg_guidance, sdxl_indexing=True,
+                                   tables_on_device=(self.schedule_kind == "lightning"))
+        return self._run_trajectory(self.step_mode, torch.float32, steps, zt.float(), null_prompt_embeds,
+                                    prompt_embeds, add_cond_kwargs, callback_fn, 'z0t')
+
+
+@register_solver('euler')
+class Euler(SDXL):
+    """Karras Euler (VE casted), plain CFG, Karras sigmas (latent_sdxl.py:469-517)."""
+    quantize = True
+
+    @torch.no_grad()
+    def reverse_process(self, null_prompt_embeds, prompt_embeds, cfg_guidance, add_cond_kwargs, shape=(1024, 1024),
+                        callback_fn=None, **kwargs):
+        ts = self.total_sigmas()
+        sigmas = K.get_sigmas_karras(len(self.scheduler.timesteps), ts.min(), ts.max(), rho=7.)
+        zt = kwargs.get('xT')
+        if zt is None:
+            zt_dim = (1, 4, shape[1] // self.vae_scale_factor, shape[0] // self.vae_scale_factor)
+            zt = self.initialize_latent(method="random_kdiffusion", latent_dim=zt_dim, sigmas=sigmas)
+        z0t, _ = K.euler_cfgpp_loop(self, zt.to(torch.float16), sigmas, cfg_guidance,
+                                    (null_prompt_embeds, prompt_embeds, add_cond_kwargs), callback_fn, cfgpp=False)
+        return z0t
+
+
+@register_solver('ddim_lightning')
+class BaseDDIMLight(BaseDDIM, SDXLLightning):
+    def __init__(self, **kwargs):
+        SDXLLightning.__init__(self, **kwargs)
+
+    def reverse_process(self, null_prompt_embeds, prompt_embeds, cfg_guidance, add_cond_kwargs, shape=(1024, 1024),
+                        callback_fn=None, **kwargs):
+        assert cfg_guidance == 1.0, "CFG should be turned off in the lightning version"
+        return super().reverse_process(null_prompt_embeds, prompt_embeds, cfg_guidance, add_cond_kwargs, shape,
+                                       callback_fn, **kwargs)
+
+
+@register_solver('euler_lightning')
+class EulerLight(Euler, SDXLLightning):
+    quantize = True
+
+    def __init__(self, **kwargs):
+        SDXLLightning.__init__(self, **kwargs)
+
+    def reverse_process(self, null_prompt_embeds, prompt_embeds, cfg_guidance, add_cond_kwargs, shape=(1024, 1024),
+                        callback_fn=None, **kwargs):
+        assert cfg_guidance == 1.0, "CFG should be turned off in the lightning version"
+        return super().reverse_process(null_prompt_embeds, prompt_embeds, cfg_guidance, add_cond_kwargs, shape,
+                                       callback_fn, **kwargs)
 
 
 ###########################################
@@ -433,9 +506,20 @@ class EulerCFGppLight(EulerCFGpp, SDXLLightning):
                                        callback_fn, **kwargs)
 
 
+@register_solver("ddim_edit")
 class EditWardSwapDDIM(SDXL):
-    """Three-prompt front end of the editing solvers (prompt = [null, source, target]) — latent_sdxl.py:570-655.
-    Subclasses provide `inversion` and `reverse_process`."""
+    """Three-prompt front end of the editing solvers (prompt = [null, source, target]) — latent_sdxl.py:570-655 — and
+    the plain-CFG edit loop (:656-707): plain inversion under the source prompt, plain DDIM under the target prompt,
+    both through `alpha()` with the fp16 VAE latent as state (fused step mode STEP_DDIM_CFG)."""
+
+    def reverse_process(self, null_prompt_embeds, src_prompt_embeds, tgt_prompt_embed, cfg_guidance,
+                        add_src_cond_kwargs, add_tgt_cond_kwargs, callback_fn=None, **kwargs):
+        zt = self.initialize_latent(method='ddim', src_img=kwargs.get('src_img', None), uc=null_prompt_embeds,
+                                    c=src_prompt_embeds, cfg_guidance=cfg_guidance,
+                                    add_cond_kwargs=add_src_cond_kwargs)
+        steps = S.ddim_cfgpp_steps(self._sch, cfg_guidance, sdxl_indexing=False)
+        return self._run_trajectory(S.STEP_DDIM_CFG, zt.dtype, steps, zt, null_prompt_embeds, tgt_prompt_embed,
+                                    add_tgt_cond_kwargs, callback_fn, 'z0t')
 
     def sample(self,
                prompt1=["", "", ""],

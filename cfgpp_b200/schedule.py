@@ -21,7 +21,7 @@ import torch
 
 NUM_TRAIN_TIMESTEPS = 1000
 
-STEP_NONE, STEP_DDIM_CFGPP, STEP_DDIM_INV_CFGPP, STEP_DPMPP2M_CFGPP = 0, 1, 2, 3
+STEP_NONE, STEP_DDIM_CFGPP, STEP_DDIM_INV_CFGPP, STEP_DPMPP2M_CFGPP, STEP_DDIM_CFG = 0, 1, 2, 3, 4
 F16, F32 = 0, 1
 
 

@@ -58,6 +58,7 @@ typedef struct cfgpp_model_desc {
 #define CFGPP_STEP_DDIM_CFGPP 1      /* ddim_cfg++ (+_lightning)  latent_diffusion.py:660-666, latent_sdxl.py:738-744 */
 #define CFGPP_STEP_DDIM_INV_CFGPP 2  /* inversion of ddim_inversion_cfg++  latent_diffusion.py:904-908 */
 #define CFGPP_STEP_DPMPP2M_CFGPP 3   /* dpm++_2m_cfgpp  latent_sdxl.py:902-919 */
+#define CFGPP_STEP_DDIM_CFG 4        /* plain-CFG ddim step and inversion step (baselines)  latent_diffusion.py:283-287 */
 
 /* Per-step scalars, computed by the host exactly as the reference computes them (fp32 torch CPU ops). */
 typedef struct cfgpp_step_coef {

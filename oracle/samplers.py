@@ -219,15 +219,17 @@ def karras_sigmas(tb: ScheduleTables):
 
 
 @torch.no_grad()
-def kd_euler_cfgpp(unet, tb, x, sigmas, uc, c, cfg_guidance, add_cond_kwargs=None, ancestral=False):
+def kd_euler_cfgpp(unet, tb, x, sigmas, uc, c, cfg_guidance, add_cond_kwargs=None, ancestral=False, plus=True):
     """The loop body shared by euler_cfg++ (latent_diffusion.py:701-711, latent_sdxl.py:787-799) and euler_a_cfg++
-    (latent_diffusion.py:745-755). x is the scaled fp16 start state. Returns (last denoised, x)."""
+    (latent_diffusion.py:745-755). x is the scaled fp16 start state. Returns (last denoised, x).
+    plus=False: the plain-CFG `euler` / `euler_a` (latent_diffusion.py:322-330, :366-379; latent_sdxl.py:497-507) —
+    the ODE derivative takes the guided estimate."""
     denoised = None
     for i in range(len(sigmas) - 1):
         sigma = sigmas[i]
         t = kd_timestep(tb, sigma).to(x.device)
         denoised, uncond_denoised = kd_denoised(unet, x, sigma, t, uc, c, cfg_guidance, add_cond_kwargs)
-        d = (x - uncond_denoised) / sigma.item()
+        d = (x - (uncond_denoised if plus else denoised)) / sigma.item()
         if ancestral:
             sigma_down, sigma_up = ancestral_step(sigmas[i], sigmas[i + 1])
             x = denoised + d * sigma_down
@@ -239,8 +241,8 @@ def kd_euler_cfgpp(unet, tb, x, sigmas, uc, c, cfg_guidance, add_cond_kwargs=Non
 
 
 @torch.no_grad()
-def kd_dpmpp_2s_a_cfgpp(unet, tb, x, sigmas, uc, c, cfg_guidance):
-    """latent_diffusion.py:786-817."""
+def kd_dpmpp_2s_a_cfgpp(unet, tb, x, sigmas, uc, c, cfg_guidance, plus=True):
+    """latent_diffusion.py:786-817; plus=False: plain `dpm++_2s_a`, latent_diffusion.py:410-437."""
     t_fn = lambda sigma: sigma.log().neg()  # noqa: E731
     sigma_fn = lambda t: t.neg().exp()      # noqa: E731
     denoised = None
@@ -249,28 +251,32 @@ def kd_dpmpp_2s_a_cfgpp(unet, tb, x, sigmas, uc, c, cfg_guidance):
         new_t = kd_timestep(tb, sigma).to(x.device)
         denoised, uncond_denoised = kd_denoised(unet, x, sigma, new_t, uc, c, cfg_guidance)
         sigma_down, sigma_up = ancestral_step(sigmas[i], sigmas[i + 1])
+        first = uncond_denoised if plus else denoised
         if sigma_down == 0:
-            d = (x - uncond_denoised) / sigmas[i].item()
+            d = (x - first) / sigmas[i].item()
             x = denoised + d * sigma_down
         else:
             t, t_next = t_fn(sigmas[i]), t_fn(sigma_down)
             r = 1 / 2
             h = t_next - t
             s = t + r * h
-            x_2 = (sigma_fn(s) / sigma_fn(t)) * x - (-h * r).expm1() * uncond_denoised
+            x_2 = (sigma_fn(s) / sigma_fn(t)) * x - (-h * r).expm1() * first
             sigma_s = sigma_fn(s)
             t_2 = kd_timestep(tb, sigma_s).to(x.device)
             denoised_2, uncond_denoised_2 = kd_denoised(unet, x_2, sigma_s, t_2, uc, c, cfg_guidance)
-            x = denoised_2 - torch.exp(-h) * uncond_denoised_2 + (sigma_fn(t_next) / sigma_fn(t)) * x
+            if plus:
+                x = denoised_2 - torch.exp(-h) * uncond_denoised_2 + (sigma_fn(t_next) / sigma_fn(t)) * x
+            else:
+                x = (sigma_fn(t_next) / sigma_fn(t)) * x - (-h).expm1() * denoised_2
         if sigmas[i + 1] > 0:
             x = x + torch.randn_like(x) * sigma_up
     return denoised, x
 
 
 @torch.no_grad()
-def kd_dpmpp_2m_cfgpp_sd15(unet, tb, x, sigmas, uc, c, cfg_guidance):
+def kd_dpmpp_2m_cfgpp_sd15(unet, tb, x, sigmas, uc, c, cfg_guidance, plus=True):
     """latent_diffusion.py:848-866 — second-order term on (denoised - old_denoised) (the SDXL file uses
-    uncond_denoised there, see sdxl_dpmpp_2m_cfgpp above)."""
+    uncond_denoised there, see sdxl_dpmpp_2m_cfgpp above). plus=False: plain `dpm++_2m`, latent_diffusion.py:470-487."""
     t_fn = lambda sigma: sigma.log().neg()  # noqa: E731
     old_denoised = None
     denoised = None
@@ -280,15 +286,16 @@ def kd_dpmpp_2m_cfgpp_sd15(unet, tb, x, sigmas, uc, c, cfg_guidance):
         denoised, uncond_denoised = kd_denoised(unet, x, sigma, new_t, uc, c, cfg_guidance)
         t, t_next = t_fn(sigmas[i]), t_fn(sigmas[i + 1])
         h = t_next - t
+        lead = uncond_denoised if plus else denoised
         if old_denoised is None or sigmas[i + 1] == 0:
-            x = denoised + (x - uncond_denoised) / sigmas[i].item() * sigmas[i + 1]
+            x = denoised + (x - lead) / sigmas[i].item() * sigmas[i + 1]
         else:
             h_last = t - t_fn(sigmas[i - 1])
             r = h_last / h
-            extra1 = -torch.exp(-h) * uncond_denoised - (-h).expm1() * (denoised - old_denoised) / (2 * r)
+            extra1 = -torch.exp(-h) * lead - (-h).expm1() * (denoised - old_denoised) / (2 * r)
             extra2 = torch.exp(-h) * x
             x = denoised + extra1 + extra2
-        old_denoised = uncond_denoised
+        old_denoised = lead
     return denoised, x
 
 
@@ -326,3 +333,50 @@ def ddim_edit_cfgpp(unet, tb, z0_src, uc, c_src, c_tgt, cfg_guidance, add_src=No
         z0t = (zt - (1 - at).sqrt() * noise_pred) / at.sqrt()
         zt = at_next.sqrt() * z0t + (1 - at_next).sqrt() * noise_uc
     return zT, z0t
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# plain-CFG DDIM baselines (renoise with the guided eps) — latent_diffusion.py:160-182 (inversion),
+# :247-299 (ddim), :506-612 (ddim_inversion / ddim_edit); latent_sdxl.py:301-324, :425-467, :656-707.
+# ------------------------------------------------------------------------------------------------------------------
+
+@torch.no_grad()
+def ddim_plain(unet, tb, zT, uc, c, cfg_guidance, add_cond_kwargs=None, sdxl_indexing=False, record=None):
+    """BaseDDIM: SD v1.5 indexes through alpha() (latent_diffusion.py:275-287), SDXL through the raw table with the
+    negative-index wrap on the last step (latent_sdxl.py:443-455)."""
+    zt, z0t = zT, None
+    ts = tb.timesteps.int() if sdxl_indexing else tb.timesteps
+    for t in ts:
+        if sdxl_indexing:
+            at, at_next = tb.alphas_cumprod[t], tb.alphas_cumprod[t - tb.skip]
+        else:
+            at, at_next = _alpha_sd15(tb, t), _alpha_sd15(tb, t - tb.skip)
+        noise_uc, noise_c = predict_noise(unet, zt, t.to(zt.device), uc, c, add_cond_kwargs)
+        noise_pred = noise_uc + cfg_guidance * (noise_c - noise_uc)
+        if record is not None:
+            record.append({"zt": zt.clone(), "noise_uc": noise_uc.clone(), "noise_c": noise_c.clone()})
+        z0t = (zt - (1 - at).sqrt() * noise_pred) / at.sqrt()
+        zt = at_next.sqrt() * z0t + (1 - at_next).sqrt() * noise_pred
+    return z0t
+
+
+@torch.no_grad()
+def ddim_inversion_plain(unet, tb, z0, uc, c, cfg_guidance, add_cond_kwargs=None):
+    """StableDiffusion.inversion / SDXL.inversion (latent_diffusion.py:160-182, latent_sdxl.py:301-324)."""
+    if add_cond_kwargs is not None and (cfg_guidance == 0.0 or cfg_guidance == 1.0):
+        add_cond_kwargs = {k: v[-1].unsqueeze(0) for k, v in add_cond_kwargs.items()}
+    zt = z0.clone()
+    for t in reversed(tb.timesteps):
+        at, at_prev = _alpha_sd15(tb, t), _alpha_sd15(tb, t - tb.skip)
+        noise_uc, noise_c = predict_noise(unet, zt, t.to(zt.device), uc, c, add_cond_kwargs)
+        noise_pred = noise_uc + cfg_guidance * (noise_c - noise_uc)
+        z0t = (zt - (1 - at_prev).sqrt() * noise_pred) / at_prev.sqrt()
+        zt = at.sqrt() * z0t + (1 - at).sqrt() * noise_pred
+    return zt
+
+
+@torch.no_grad()
+def ddim_edit_plain(unet, tb, z0_src, uc, c_src, c_tgt, cfg_guidance, add_src=None, add_tgt=None):
+    """ddim_edit (c_tgt != c_src) / ddim_inversion (c_tgt == c_src): plain inversion, then plain DDIM through alpha()."""
+    zT = ddim_inversion_plain(unet, tb, z0_src, uc, c_src, cfg_guidance, add_src)
+    return zT, ddim_plain(unet, tb, zT, uc, c_tgt, cfg_guidance, add_tgt, sdxl_indexing=False)

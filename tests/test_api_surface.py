@@ -19,6 +19,13 @@ def test_registries_mirror_reference_names_and_errors():
     # the rest of the CFG++ --method surface
     assert {"euler_cfg++", "euler_a_cfg++", "dpm++_2s_a_cfg++", "dpm++_2m_cfg++", "ddim_edit_cfg++"} <= set(LD.__SOLVER__)
     assert {"euler_cfg++", "euler_cfg++_lightning", "dpm++_2m_cfgpp_lightning", "ddim_edit_cfg++"} <= set(LX.__SOLVER__)
+    # section 8 f4: the plain-CFG baselines -> the registries now equal the reference's --method surface
+    assert set(LD.__SOLVER__) == {"ddim", "euler", "euler_a", "dpm++_2s_a", "dpm++_2m", "ddim_inversion", "ddim_edit",
+                                  "ddim_cfg++", "euler_cfg++", "euler_a_cfg++", "dpm++_2s_a_cfg++", "dpm++_2m_cfg++",
+                                  "ddim_inversion_cfg++", "ddim_edit_cfg++"}
+    assert set(LX.__SOLVER__) == {"ddim", "euler", "ddim_lightning", "euler_lightning", "ddim_edit", "ddim_cfg++",
+                                  "euler_cfg++", "euler_cfg++_lightning", "ddim_cfg++_lightning", "dpm++_2m_cfgpp",
+                                  "dpm++_2m_cfgpp_lightning", "ddim_edit_cfg++"}
     with pytest.raises(ValueError, match="does not exist"):
         LX.get_solver("no_such_solver")
     with pytest.raises(ValueError, match="already registered"):

@@ -318,3 +318,83 @@ def test_sdxl_euler_and_edit_cfgpp_vs_oracle():
                            unet_config=cfg)
     out = le.reverse_process(uc, c, 1.0, {k: v[-1:].clone() for k, v in add.items()}, shape=(8 * hw, 8 * hw))
     assert out.shape == (1, 4, hw, hw) and torch.isfinite(out).all()
+
+
+# ---- plain-CFG baselines (fused STEP_DDIM_CFG mode, plain k-diffusion loops) -----------------
+
+def test_step_kernel_plain_cfg_matches_reference_arithmetic():
+    from cfgpp_b200 import _native as nv, schedule as S
+    g = torch.Generator().manual_seed(3)
+    sch = S.Schedule.make(50)
+    st = S.ddim_cfgpp_steps(sch, 7.5, True)[11]
+    t = int(st.t)
+    at, an = sch.alphas_cumprod[t], sch.alphas_cumprod[t - sch.skip]
+    zt = torch.randn(2, 4, 32, 32, generator=g).to(dev)
+    eu = torch.randn(2, 4, 32, 32, generator=g).half().to(dev)
+    ec = torch.randn(2, 4, 32, 32, generator=g).half().to(dev)
+    npred = eu + 7.5 * (ec - eu)                              # latent_sdxl.py:449
+    z0_ref = (zt - (1 - at).sqrt() * npred) / at.sqrt()       # :452
+    zn_ref = an.sqrt() * z0_ref + (1 - an).sqrt() * npred     # :455 (guided eps, not eps_uc)
+    z = zt.clone()
+    z0 = nv.op_cfgpp_step(eu, ec, S.STEP_DDIM_CFG, st.coef, z)
+    assert (z0 - z0_ref).abs().max() <= 1e-6 * z0_ref.abs().max()
+    assert (z - zn_ref).abs().max() <= 1e-6 * zn_ref.abs().max()
+    # fp16 state (the inversion / edit loops start from the VAE latent)
+    inv = S.ddim_inversion_cfgpp_steps(sch, 7.5)[5]
+    t = int(inv.t)
+    at, ap = sch.alpha(t), sch.alpha(t - sch.skip)
+    zh = torch.randn(1, 4, 32, 32, generator=g).half().to(dev)
+    eu, ec = eu[:1].contiguous(), ec[:1].contiguous()
+    npred = eu + 7.5 * (ec - eu)
+    z0_ref = (zh - (1 - ap).sqrt() * npred) / ap.sqrt()       # latent_diffusion.py:179
+    zn_ref = at.sqrt() * z0_ref + (1 - at).sqrt() * npred     # :180
+    z = zh.clone()
+    nv.op_cfgpp_step(eu, ec, S.STEP_DDIM_CFG, inv.coef, z)
+    assert z.dtype == torch.float16 and ((z.float() - zn_ref.float()).abs() <= 2 * _ulp16(zn_ref)).all()
+
+
+def test_plain_cfg_solvers_vs_oracle():
+    from cfgpp_b200 import latent_diffusion as LD, latent_sdxl as LX
+    from oracle import samplers as OSm, schedule as OS
+    # SDXL: fused plain ddim (fp32 state) and Karras euler
+    cfg, sd, net, ref = build_pair("tiny_sdxl", dev)
+    net.close()
+    nfe, lam, hw = 6, 2.0, 32
+    z, uc, c, add = make_inputs(cfg, 1, hw, dev)
+    tb = OS.make_tables(nfe)
+    kw = dict(solver_config=SimpleNamespace(num_sampling=nfe), device=dev, unet_config=cfg, state_dict=sd)
+    z0_ref = OSm.ddim_plain(ref, tb, z, uc, c, lam, add, sdxl_indexing=True)
+    z0 = LX.get_solver("ddim", **kw).reverse_process(uc, c, lam, add, shape=(8 * hw, 8 * hw), zT=z)
+    e = rel_l2(z0, z0_ref)
+    print(f"sdxl ddim (plain CFG, lambda={lam}): rel-L2 final z0t {e:.3e}")
+    assert z0.dtype == torch.float32 and e <= 3e-2
+    sig = OSm.karras_sigmas(tb)
+    x0 = OSm.kd_start_state(z, sig)
+    d_ref, _ = OSm.kd_euler_cfgpp(ref, tb, x0.clone(), sig, uc, c, lam, add, plus=False)
+    d = LX.get_solver("euler", **kw).reverse_process(uc, c, lam, add, shape=(8 * hw, 8 * hw), xT=x0.clone())
+    e = rel_l2(d, d_ref)
+    print(f"sdxl euler (plain CFG): rel-L2 last z0t {e:.3e}")
+    assert e <= 3e-2
+    # SD v1.5: plain inversion + edit on the fused mode (fp16 state), one plain k-diffusion sampler
+    cfg, sd, net, ref = build_pair("tiny_sd15", dev)
+    net.close()
+    z, uc, c, _ = make_inputs(cfg, 1, hw, dev)
+    g = torch.Generator().manual_seed(9)
+    c_tgt = torch.randn(1, 77, cfg.cross_attention_dim, generator=g).half().to(dev)
+    kw = dict(solver_config=SimpleNamespace(num_sampling=nfe), device=dev, unet_config=cfg, state_dict=sd)
+    ed = LD.get_solver("ddim_edit", **kw)
+    z0_src = (0.4 * z).half()
+    zT_ref, z0t_ref = OSm.ddim_edit_plain(ref, tb, z0_src, uc, c, c_tgt, lam)
+    zT = ed.inversion(z0_src, uc, c, lam)
+    z0t = ed.reverse_process(uc, c_tgt, lam, zT)
+    print(f"sd15 ddim_edit (plain CFG): rel-L2 zT {rel_l2(zT, zT_ref):.3e}, edited z0t {rel_l2(z0t, z0t_ref):.3e}")
+    assert zT.dtype == torch.float16 and rel_l2(zT, zT_ref) <= 3e-2 and rel_l2(z0t, z0t_ref) <= 3e-2
+    s2 = LD.get_solver("dpm++_2s_a", **kw)
+    sig = s2.karras_sigmas()
+    x0 = OSm.kd_start_state(z, sig)
+    torch.manual_seed(77)
+    _, x_ref = OSm.kd_dpmpp_2s_a_cfgpp(ref, tb, x0.clone(), sig, uc, c, lam, plus=False)
+    torch.manual_seed(77)
+    _, x = s2.reverse_process(uc, c, lam, x0.clone())
+    print(f"sd15 dpm++_2s_a (plain CFG): rel-L2 final x {rel_l2(x, x_ref):.3e}")
+    assert rel_l2(x, x_ref) <= 3e-2

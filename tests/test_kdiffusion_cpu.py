@@ -51,31 +51,33 @@ def _close16(a, b, ulps=2):
     return bool(((a - b).abs() <= tol).all())
 
 
+@pytest.mark.parametrize("plus", [True, False])
 @pytest.mark.parametrize("ancestral", [False, True])
-def test_product_euler_loops_match_oracle(ancestral):
+def test_product_euler_loops_match_oracle(ancestral, plus):
     tb, noise, uc, c, unet = _setup()
     sigmas = OSm.karras_sigmas(tb)
     assert torch.equal(sigmas, K.get_sigmas_karras(len(tb.timesteps), tb.sigmas.min(), tb.sigmas.max(), rho=7.))
     x0 = OSm.kd_start_state(noise, sigmas)
     torch.manual_seed(11)
-    d_ref, x_ref = OSm.kd_euler_cfgpp(unet, tb, x0.clone(), sigmas, uc, c, 0.6, ancestral=ancestral)
+    d_ref, x_ref = OSm.kd_euler_cfgpp(unet, tb, x0.clone(), sigmas, uc, c, 0.6, ancestral=ancestral, plus=plus)
     torch.manual_seed(11)
-    d, x = K.euler_cfgpp_loop(StubSolver(tb, unet), x0.clone(), sigmas, 0.6, (uc, c), ancestral=ancestral)
+    d, x = K.euler_cfgpp_loop(StubSolver(tb, unet), x0.clone(), sigmas, 0.6, (uc, c), ancestral=ancestral, cfgpp=plus)
     assert x.dtype == torch.float16 and _close16(x, x_ref) and _close16(d, d_ref)
 
 
-def test_product_dpmpp_loops_match_oracle():
+@pytest.mark.parametrize("plus", [True, False])
+def test_product_dpmpp_loops_match_oracle(plus):
     tb, noise, uc, c, unet = _setup(nfe=7)
     sigmas = OSm.karras_sigmas(tb)
     x0 = OSm.kd_start_state(noise, sigmas)
     s = StubSolver(tb, unet)
     torch.manual_seed(5)
-    d_ref, x_ref = OSm.kd_dpmpp_2s_a_cfgpp(unet, tb, x0.clone(), sigmas, uc, c, 0.6)
+    d_ref, x_ref = OSm.kd_dpmpp_2s_a_cfgpp(unet, tb, x0.clone(), sigmas, uc, c, 0.6, plus=plus)
     torch.manual_seed(5)
-    d, x = K.dpmpp_2s_a_cfgpp_loop(s, x0.clone(), sigmas, 0.6, (uc, c))
+    d, x = K.dpmpp_2s_a_cfgpp_loop(s, x0.clone(), sigmas, 0.6, (uc, c), cfgpp=plus)
     assert _close16(x, x_ref) and _close16(d, d_ref)
-    d_ref, x_ref = OSm.kd_dpmpp_2m_cfgpp_sd15(unet, tb, x0.clone(), sigmas, uc, c, 0.6)
-    d, x = K.dpmpp_2m_cfgpp_karras_loop(s, x0.clone(), sigmas, 0.6, (uc, c))
+    d_ref, x_ref = OSm.kd_dpmpp_2m_cfgpp_sd15(unet, tb, x0.clone(), sigmas, uc, c, 0.6, plus=plus)
+    d, x = K.dpmpp_2m_cfgpp_karras_loop(s, x0.clone(), sigmas, 0.6, (uc, c), cfgpp=plus)
     assert _close16(x, x_ref) and _close16(d, d_ref)
 
 
@@ -135,3 +137,24 @@ def test_edit_loop_round_trip_with_identical_prompts():
     assert zT.dtype == torch.float16 and z0t.dtype == torch.float16
     assert float((z0t.float() - z0.float()).norm() / z0.float().norm()) < 0.25
     assert not torch.equal(zT, z0)
+
+
+def test_plain_and_plus_coincide_without_guidance_gap_and_differ_otherwise():
+    """eps_uc == eps_c: CFG and CFG++ are the same sampler; with a gap and lambda != 0 they are not."""
+    tb, noise, uc, c, unet = _setup()
+    sigmas = OSm.karras_sigmas(tb)
+    x0 = OSm.kd_start_state(noise, sigmas)
+    for fn in (OSm.kd_euler_cfgpp, OSm.kd_dpmpp_2m_cfgpp_sd15):
+        a = fn(unet, tb, x0.clone(), sigmas, uc, uc, 0.6, plus=True)[1]
+        b = fn(unet, tb, x0.clone(), sigmas, uc, uc, 0.6, plus=False)[1]
+        assert _close16(a, b, ulps=4)
+        a = fn(unet, tb, x0.clone(), sigmas, uc, c, 0.6, plus=True)[1]
+        b = fn(unet, tb, x0.clone(), sigmas, uc, c, 0.6, plus=False)[1]
+        assert not _close16(a, b, ulps=4)
+    # DDIM: plain CFG == CFG++ when lambda = 0 ... no: CFG++ renoises with eps_uc, plain with the guided eps, which
+    # coincide exactly when lambda = 0
+    z = noise
+    a = OSm.sd15_ddim_cfgpp(unet, tb, z, uc, c, 0.0)
+    b = OSm.ddim_plain(unet, tb, z, uc, c, 0.0)
+    assert torch.equal(a, b)
+    assert not torch.equal(OSm.sd15_ddim_cfgpp(unet, tb, z, uc, c, 0.6), OSm.ddim_plain(unet, tb, z, uc, c, 0.6))
