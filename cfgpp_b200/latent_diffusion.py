@@ -275,8 +275,11 @@ class _KarrasCFGpp(StableDiffusion):
         return K.get_sigmas_karras(len(self.scheduler.timesteps), ts.min(), ts.max(), rho=7.)
 
     @torch.no_grad()
-    def reverse_process(self, uc, c, cfg_guidance, x=None, callback_fn=None):
+    def reverse_process(self, uc, c, cfg_guidance, x=None, callback_fn=None, noise=None):
+        """`x`: a ready (scaled) start state; `noise`: an N(0,1) draw to scale (the `zT` every solver accepts)."""
         sigmas = self.karras_sigmas()
+        if x is None and noise is not None:
+            x = noise.to(self.device) * (sigmas[0] ** 2 + 1) ** 0.5
         if x is None:
             x = self.initialize_latent(method="random_kdiffusion", sigmas=sigmas,
                                        latent_dim=(1, 4, self.cfg.sample_size, self.cfg.sample_size))
@@ -284,7 +287,7 @@ class _KarrasCFGpp(StableDiffusion):
 
     def sample(self, cfg_guidance, prompt=["", ""], callback_fn=None, **kwargs):
         uc, c = self.get_text_embed(null_prompt=prompt[0], prompt=prompt[1])
-        denoised, x = self.reverse_process(uc, c, cfg_guidance, kwargs.get('xT'), callback_fn)
+        denoised, x = self.reverse_process(uc, c, cfg_guidance, kwargs.get('xT'), callback_fn, kwargs.get('zT'))
         img = self.decode(x if self.decode_state else denoised)
         img = (img / 2 + 0.5).clamp(0, 1)
         return img.detach().cpu()

@@ -358,6 +358,8 @@ class Euler(SDXL):
         ts = self.total_sigmas()
         sigmas = K.get_sigmas_karras(len(self.scheduler.timesteps), ts.min(), ts.max(), rho=7.)
         zt = kwargs.get('xT')
+        if zt is None and kwargs.get('zT') is not None:  # an N(0,1) draw, as every other solver accepts it
+            zt = kwargs['zT'].to(self.device) * (sigmas[0] ** 2 + 1) ** 0.5
         if zt is None:
             zt_dim = (1, 4, shape[1] // self.vae_scale_factor, shape[0] // self.vae_scale_factor)
             zt = self.initialize_latent(method="random_kdiffusion", latent_dim=zt_dim, sigmas=sigmas)
@@ -484,6 +486,8 @@ class EulerCFGpp(SDXL):
         sigmas = total_sigmas[torch.round(self.scheduler.timesteps.cpu()).int()]
         sigmas = torch.cat([sigmas, torch.tensor([0.0])])
         zt = kwargs.get('xT')
+        if zt is None and kwargs.get('zT') is not None:  # an N(0,1) draw, as every other solver accepts it
+            zt = kwargs['zT'].to(self.device) * (sigmas[0] ** 2 + 1) ** 0.5
         if zt is None:
             zt_dim = (1, 4, shape[1] // self.vae_scale_factor, shape[0] // self.vae_scale_factor)
             zt = self.initialize_latent(method="random_kdiffusion", latent_dim=zt_dim, sigmas=sigmas)
