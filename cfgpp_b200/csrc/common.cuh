@@ -58,7 +58,7 @@ CFGPP_DEVICE uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #define CFGPP_MBAR_SLEEP_NS 1000000
 #endif
 // Probe with a suspend-time hint: the thread may sleep in hardware for up to ~1 ms waiting for the phase, instead
-// of spinning through the issue stage (128 epilogue threads per SM wait for a whole main loop on tmem_full).
+// of spinning through the issue stage (the epilogue warps of an SM wait for a whole main loop on tmem_full).
 CFGPP_DEVICE uint32_t mbar_try_wait_sleep(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(

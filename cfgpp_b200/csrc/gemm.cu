@@ -1,9 +1,10 @@
 // cfgpp_b200 — persistent, warp-specialised tcgen05 GEMM / implicit-GEMM conv3x3 kernel for sm_100a.
-// See gemm.cuh for the operator contract. Structure per CTA (256 threads, 1 CTA / SM, persistent over tiles):
-//   warps 0..3 : epilogue      (tcgen05.ld 32x32b -> bias/addend/GEGLU -> fp16 smem staging -> TMA store)
-//   warp 4     : TMA producer  (A tile 128x64, B tile BNx64 per stage, 128B swizzle, mbarrier complete_tx)
-//   warp 5     : MMA issuer    (tcgen05.mma kind::f16, M=128 (256 for a CTA pair), N=BN, K=16 x4 per stage)
-//   warp 6     : TMEM allocator
+// See gemm.cuh for the operator contract. Structure per CTA (384 threads, 1 CTA / SM, persistent over tiles):
+//   warps 0..7 : epilogue      (tcgen05.ld 32x32b -> bias/addend/GEGLU/LN-fold -> fp16 smem staging -> TMA store; warp w
+//                               owns TMEM lane quarter w % 4 and the 32-column chunks of parity w / 4, end to end)
+//   warp 8     : TMA producer  (A tile 128x64, B tile BNx64 per stage, 128B swizzle, mbarrier complete_tx)
+//   warp 9     : MMA issuer    (tcgen05.mma kind::f16, M=128 (256 for a CTA pair), N=BN, K=16 x4 per stage)
+//   warp 10    : TMEM allocator
 // The producer and issuer warps run their loops warp-wide and issue from one elected lane (see elect_one()).
 // Pipelines: smem ring full/empty (TMA <-> MMA) and a 2-deep TMEM accumulator ring full/empty (MMA <-> epilogue),
 // so the epilogue of tile i overlaps the main loop of tile i+1.
