@@ -72,3 +72,26 @@ def test_forward_is_deterministic_and_rows_independent():
     s = net.predict_noise(z[:1], 500.0)
     assert rel_l2(s[0], a[0][:1]) < 1e-3 and rel_l2(s[1], a[1][:1]) < 1e-3
     net.close()
+
+
+@pytest.mark.parametrize("name", ["tiny_sdxl", "tiny_sd15"])
+def test_native_unet_against_committed_golden(name):
+    """Native forward vs the COMMITTED fp32-oracle vectors (tests/golden/r01_golden.pt): same seeded CPU weights, same
+    inputs; stated tolerance rel-L2 <= 5e-3 (fp16 path against an fp32 result)."""
+    from pathlib import Path
+    from cfgpp_b200 import config as C, weights as Wt
+    from cfgpp_b200.engine import NativeUNet
+    gold = torch.load(Path(__file__).parent / "golden" / "r01_golden.pt", weights_only=False)["unet"][name]
+    cfg = C.CONFIGS[name]()
+    sd = {k: v.to(dev) for k, v in Wt.synthetic_state_dict(cfg, seed=gold["seed"], device="cpu").items()}
+    net = NativeUNet(cfg, sd, dev)
+    hw = gold["hw"]
+    net.prepare(1, hw, hw)
+    add = gold["add"]
+    net.set_prompt(gold["ctx"].to(dev), None if add is None else add["text_embeds"].to(dev),
+                   None if add is None else add["time_ids"].float().to(dev))
+    eu, ec = net.predict_noise(gold["z"].to(dev), float(gold["t"]))
+    e_uc, e_c = rel_l2(eu.cpu(), gold["eps_uc"]), rel_l2(ec.cpu(), gold["eps_c"])
+    print(f"{name} vs golden fp32: rel-L2 eps_uc {e_uc:.3e} eps_c {e_c:.3e}")
+    assert e_uc <= 5e-3 and e_c <= 5e-3
+    net.close()
