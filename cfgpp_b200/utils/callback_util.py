@@ -1,8 +1,11 @@
 """Per-step callback protocol of the reference (utils/callback_util.py:8-37, 67-75): a callback is called as
 `callback_fn(step, t, {'z0t', 'zt', 'decode'}) -> dict` at the end of a step and may replace `z0t` / `zt`.
 Installing one makes the solvers use the un-fused seam so both tensors are materialised every step. The two
-image-dumping callbacks of the reference (draw_tweedie / draw_noisy) are debug tooling outside the hot path."""
+image-dumping callbacks of the reference (draw_tweedie / draw_noisy, :39-65) decode the Tweedie estimate / the noisy
+latent of a step and write it under <workdir>/record/."""
 from pathlib import Path
+
+import torch
 
 __CALLBACK__ = {}
 
@@ -47,6 +50,38 @@ class RecordCallback(DiffusionCallback):
     def callback(self, step, t, callback_kwargs):
         self.records.append((step, int(t), callback_kwargs["z0t"].detach().cpu(), callback_kwargs["zt"].detach().cpu()))
         return callback_kwargs
+
+
+class _DrawCallback(DiffusionCallback):
+    """Decode one of the step's latents and dump it (PNG through torchvision when importable, the tensor otherwise)."""
+    key, folder, prefix = "z0t", "tweedie", "x0"
+
+    def __init__(self, frequency: int, workdir: Path):
+        super().__init__(frequency, workdir)
+        self.outdir = Path(workdir).joinpath("record", self.folder)
+        self.outdir.mkdir(parents=True, exist_ok=True)
+
+    @torch.no_grad()
+    def callback(self, step, t, callback_kwargs):
+        img = callback_kwargs["decode"](callback_kwargs[self.key])
+        img = (img / 2 + 0.5).clamp(0, 1).cpu()
+        stem = self.outdir.joinpath(f"{self.prefix}_{int(t)}")
+        try:
+            from torchvision.utils import save_image
+            save_image(img, stem.with_suffix(".png"))
+        except Exception:  # torchvision is optional in this image
+            torch.save(img, stem.with_suffix(".pt"))
+        return callback_kwargs
+
+
+@register_callback("draw_tweedie")
+class DrawTweedieCallback(_DrawCallback):
+    key, folder, prefix = "z0t", "tweedie", "x0"
+
+
+@register_callback("draw_noisy")
+class DrawNoisyCallback(_DrawCallback):
+    key, folder, prefix = "zt", "noisy", "xt"
 
 
 class ComposeCallback(DiffusionCallback):

@@ -77,3 +77,16 @@ def test_step_coef_tables_are_float32_exact():
     at = sch.alphas_cumprod[t]
     assert st.coef.c0 == float((1 - at).sqrt()) and st.coef.c1 == float(at.sqrt())
     assert st.coef.lambda_ == float(torch.tensor(0.6, dtype=torch.float32))
+
+
+def test_draw_callbacks_dump_decoded_latents(tmp_path):
+    """utils/callback_util.py:39-65 of the reference: decode z0t / zt of the step, write under <workdir>/record/."""
+    import torch
+    from cfgpp_b200.utils.callback_util import ComposeCallback
+    cb = ComposeCallback(workdir=tmp_path, frequency=1, callbacks=["draw_noisy", "draw_tweedie"])
+    kw = {"z0t": torch.zeros(1, 4, 8, 8), "zt": torch.ones(1, 4, 8, 8),
+          "decode": lambda z: z[:, :3].repeat_interleave(8, 2).repeat_interleave(8, 3)}
+    out = cb(0, torch.tensor(901), kw)
+    assert out is kw
+    assert len(list((tmp_path / "record" / "tweedie").glob("x0_901.*"))) == 1
+    assert len(list((tmp_path / "record" / "noisy").glob("xt_901.*"))) == 1
