@@ -90,3 +90,26 @@ def test_draw_callbacks_dump_decoded_latents(tmp_path):
     assert out is kw
     assert len(list((tmp_path / "record" / "tweedie").glob("x0_901.*"))) == 1
     assert len(list((tmp_path / "record" / "noisy").glob("xt_901.*"))) == 1
+
+
+def test_checkpoint_resolution_round_trip(tmp_path):
+    """model_key = a diffusers-format *.safetensors file -> those exact weights; 'synthetic:<seed>' -> seeded weights;
+    an HF hub id (nothing can be downloaded here) -> synthetic with a warning."""
+    import pytest
+    import torch
+    from safetensors.torch import save_file
+    from cfgpp_b200 import weights as Wt
+    from cfgpp_b200.config import tiny_sdxl_config
+    from cfgpp_b200.latent_sdxl import resolve_state_dict
+    cfg = tiny_sdxl_config()
+    sd = Wt.synthetic_state_dict(cfg, seed=77, device="cpu")
+    path = tmp_path / "unet.safetensors"
+    save_file({k: v.contiguous() for k, v in sd.items()}, str(path))
+    back = resolve_state_dict(str(path), cfg, "cpu")
+    assert set(back) == set(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
+    assert [k for k, _, _ in Wt.unet_param_specs(cfg)] == list(sd)       # diffusers key names, spec order
+    again = resolve_state_dict("synthetic:77", cfg, "cpu")
+    assert all(torch.equal(again[k], sd[k]) for k in sd)
+    with pytest.warns(UserWarning, match="no checkpoint"):
+        other = resolve_state_dict("stabilityai/stable-diffusion-xl-base-1.0", cfg, "cpu")
+    assert set(other) == set(sd)
