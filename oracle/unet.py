@@ -19,7 +19,7 @@ reference's CUDA path (it issues the same torch ops), (c) on CPU the "repo's own
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Optional, Tuple
 
 import torch
