@@ -1,30 +1,22 @@
-// cfgpp_b200 — flash-style attention forward for head_dim 64 on tcgen05/TMEM (sm_100a). See attention.cuh.
+// cfgpp_b200 — round-2 CANDIDATE of the attention kernel: P travels softmax -> TENSOR MEMORY -> PV MMA
+// (tcgen05.st + tcgen05.mma with the A operand in TMEM) instead of through swizzled shared memory + proxy fence.
 //
-// One CTA = up to two 128-row query tiles of one (batch, head) ("ping-pong"), looping over 128-wide KV tiles that
-// both query tiles share (K / V are fetched once per pair):
-//   warp 0 lane 0 : TMA producer (Q0, Q1 once; K / V rings, 128B swizzle)
-//   warp 1 lane 0 : MMA issuer   S_q = Q_q K_j^T   (M128 N128 K64, fp32 in TMEM)
-//                                O_q += P_q V_j    (M128 N64 K128; A = P from swizzled smem, B = V MN-major).
-//                   Event driven: QK_q(j+1) is issued as soon as the softmax warps of q have pulled S_q(j) into
-//                   registers (s_free), PV_q(j) as soon as P_q(j) is in shared memory (p_full) — whichever comes
-//                   first — so neither query tile's softmax ever waits for the tensor pipe
-//   warp 2        : TMEM allocator (512 columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384))
-//   warps 4..7    : softmax of query tile 0, warps 8..11: query tile 1 — one row per thread:
-//                   a single TMEM read of the 128 scores into registers, row max, p = exp2((s - m) * scale*log2e),
-//                   fp32 row sum, P rounded to fp16 into smem. O accumulates in TMEM across KV tiles; the running
-//                   max is only advanced (and O / l rescaled, through tcgen05.ld/st) when the new maximum exceeds
-//                   the reference by more than 2^8 in the exp2 domain — exact after the final 1/l normalisation,
-//                   and p <= 256 stays well inside fp16 / fp32 range.
+// STATUS: compiles for sm_100a, NOT YET RUN on hardware as a whole; it is dispatched only when CFGPP_ATTN_TMEM_P=1 is
+// set (run_attn_op in attention.cu) and is not on the default path. The one genuinely new ingredient - the TMEM layout
+// of a K-major fp16 A operand - is proven by tools/bringup/tmem_a_mma.cu (bit-exact on B200). Everything else is
+// attention.cu unchanged: two 128-row query tiles per CTA, S / O in TMEM, event-driven issuer, lazy max rescale.
+// TMEM columns (HD = 64, two tiles): S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384) P0 [384,448) P1 [448,512).
+// What it removes per (tile, KV step): 32 KB of st.shared, the fence.proxy.async, 32 KB of MMA operand reads from smem;
+// the freed 64 KB of shared memory go to a deeper K / V ring.
 #include <cmath>
-#include <cstdlib>
 
 #include "attention.cuh"
 #include "common.cuh"
 
 namespace cfgpp {
 
-void attn_configure();
-void run_attn_tmemp(const AttnOp& op, cudaStream_t stream);  // attention_tmemp.cu (round-2 candidate, opt-in)
+void attn_tmemp_configure();
+void run_attn_tmemp(const AttnOp& op, cudaStream_t stream);
 
 namespace {
 
@@ -41,29 +33,30 @@ template <int HD, int NQT, int KS>
 struct ACfg {
   static constexpr int NA = HD / 64;                    // swizzle atoms per tile row
   static constexpr int TILE_BYTES = NA * ATOM_BYTES;    // one Q / K / V tile
-  static constexpr int P_BYTES = 2 * ATOM_BYTES;        // one P tile (128 x 128 fp16)
-  static constexpr int SMEM_BYTES = TILE_BYTES * (NQT + 2 * KS) + P_BYTES * NQT + 1024 + 256;
+  static constexpr int SMEM_BYTES = TILE_BYTES * (NQT + 2 * KS) + 1024 + 256;
   static constexpr uint32_t O_COL = NQT * 128;
+  static constexpr uint32_t P_COL = O_COL + NQT * HD;  // 64 columns per tile: 128 fp16 of P per row, two per column
+  static_assert(P_COL + NQT * 64 <= 512, "TMEM overflow");
   static_assert(NQT * 128 + NQT * HD <= 512, "TMEM overflow");
   static_assert(SMEM_BYTES <= 232448, "shared memory overflow");
 };
 
 template <int HD, int NQT, int KS>
 __global__ void __launch_bounds__(kThreads, 1)
-attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+attn_tmemp_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
             const __grid_constant__ CUtensorMap map_v) {
   using A = ACfg<HD, NQT, KS>;
   constexpr int TILE_BYTES = A::TILE_BYTES;
   constexpr int NA = A::NA;
   constexpr uint32_t O_COL = A::O_COL;
+  constexpr uint32_t P_COL = A::P_COL;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* sQ = smem;                      // NQT tiles
   uint8_t* sK = sQ + NQT * TILE_BYTES;     // KS tiles
   uint8_t* sV = sK + KS * TILE_BYTES;      // KS tiles
-  uint8_t* sP = sV + KS * TILE_BYTES;      // NQT query tiles x 2 halves of 64 columns
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NQT * A::P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KS * TILE_BYTES);
   uint64_t* q_full = bars;            // [2]
   uint64_t* k_full = q_full + 2;      // [KS]
   uint64_t* k_empty = k_full + KS;
@@ -158,11 +151,9 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
         // 8-row K groups are 1024 B apart (SBO), 64-wide N atoms 16 KB apart (LBO); a K step of 16 rows advances 2048 B.
         const uint64_t v_desc = make_sdesc_sw128(smem_u32(sV + (j % KS) * TILE_BYTES), 1024, ATOM_BYTES);
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) {
-          const uint64_t p_desc =
-              make_sdesc_sw128(smem_u32(sP + qt * A::P_BYTES + (k >> 2) * ATOM_BYTES), 1024, 0) + 2 * (k & 3);
-          umma_f16(tmem_base + O_COL + qt * HD, p_desc, v_desc + 128 * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < BKV / 16; ++k)  // A = P_q from TMEM: K step k = 16 kv rows = 8 packed columns
+          umma_f16_ts(tmem_base + O_COL + qt * HD, tmem_base + P_COL + qt * 64 + 8 * k, v_desc + 128 * k, idesc_pv,
+                      (j | k) != 0 ? 1u : 0u);
         umma_commit(&pv_done[qt]);
       };
       for (int qt = 0; qt < n_qt; ++qt) mbar_wait(&q_full[qt], 0);
@@ -214,7 +205,7 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
       const uint32_t lane_off = static_cast<uint32_t>(qw * 32) << 16;
       const uint32_t s_addr = tmem_base + qt * BKV + lane_off;
       const uint32_t o_addr = tmem_base + O_COL + qt * HD + lane_off;
-      uint8_t* prow = sP + qt * A::P_BYTES + row * 128;
+      const uint32_t p_addr = tmem_base + P_COL + qt * 64 + lane_off;
       const float c = p.scale_log2e;
       float m_ref = -INFINITY, l_run = 0.f;
 
@@ -270,23 +261,21 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
         const float mc = m_ref * c;
         float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-        for (int g = 0; g < 16; ++g) {  // 16-byte chunks of the 256-byte P row (two 128-byte halves)
-          uint32_t pk[4];
+        for (int h = 0; h < 2; ++h) {  // 64 scores -> 32 packed half2 words -> 32 TMEM columns of this row
+          uint32_t pk[32];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float p0 = fast_exp2(__uint_as_float(s[g * 8 + 2 * e]) * c - mc);
-            const float p1 = fast_exp2(__uint_as_float(s[g * 8 + 2 * e + 1]) * c - mc);
+          for (int e = 0; e < 32; ++e) {
+            const float p0 = fast_exp2(__uint_as_float(s[h * 64 + 2 * e]) * c - mc);
+            const float p1 = fast_exp2(__uint_as_float(s[h * 64 + 2 * e + 1]) * c - mc);
             rs0 += p0;
             rs1 += p1;
             pk[e] = pack_half2(p0, p1);
           }
-          const int half_idx = g >> 3;        // which 64-column half
-          const int ch = (g & 7) ^ (row & 7);  // 128B swizzle
-          *reinterpret_cast<uint4*>(prow + half_idx * ATOM_BYTES + ch * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          tmem_st_x32(p_addr + h * 32, pk);
         }
+        tmem_st_wait();
         l_run += rs0 + rs1;
         tc_fence_before();
-        fence_proxy_async_smem();
         mbar_arrive(&p_full[qt]);
       }
       mbar_wait(&pv_done[qt], (n_tiles - 1) & 1);
@@ -322,70 +311,27 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
   }
 }
 
-CUtensorMap make_head_map(const __half* base, int ld, int B, int N, int cols) {
-  uint64_t dims[3] = {(uint64_t)cols, (uint64_t)N, (uint64_t)B};
-  uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)N * ld * 2};
-  uint32_t box[3] = {64, 128, 1};
-  return make_tmap_f16(base, 3, dims, strides, box);
-}
-
-template <int HD, int NQT, int KS>
-void configure_one() {
-  CFGPP_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel<HD, NQT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        ACfg<HD, NQT, KS>::SMEM_BYTES));
-}
-
 template <int HD, int NQT, int KS>
 void launch(const AttnOp& op, cudaStream_t stream) {
   dim3 grid((op.p.Nq + NQT * BQ - 1) / (NQT * BQ), op.p.H, op.p.B);
-  launch_pdl(attn_kernel<HD, NQT, KS>, grid, dim3(kThreads), ACfg<HD, NQT, KS>::SMEM_BYTES, stream, op.p, op.map_q,
+  launch_pdl(attn_tmemp_kernel<HD, NQT, KS>, grid, dim3(kThreads), ACfg<HD, NQT, KS>::SMEM_BYTES, stream, op.p, op.map_q,
              op.map_k, op.map_v);
 }
 
 }  // namespace
 
-int attn_padded_head_dim(int head_dim) { return ((head_dim + 63) / 64) * 64; }
-
-AttnOp make_attn_op(const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, __half* out,
-                    int ldo, int B, int H, int Nq, int Nkv, int head_dim) {
-  AttnOp op{};
-  CFGPP_REQUIRE(Nkv >= 1 && Nq >= 1, "empty attention");
-  CFGPP_REQUIRE(ldo % 8 == 0, "ldo must be a multiple of 8");
-  CFGPP_REQUIRE(head_dim >= 8 && head_dim <= 192, "attention supports head_dim <= 192");
-  const int hdp = attn_padded_head_dim(head_dim);
-  op.hd_pad = hdp;
-  op.head_dim = head_dim;
-  op.p.B = B; op.p.H = H; op.p.Nq = Nq; op.p.Nkv = Nkv; op.p.ldo = ldo; op.p.out = out;
-  op.p.scale_log2e = (1.0f / sqrtf(static_cast<float>(head_dim))) * 1.4426950408889634f;
-  op.map_q = make_head_map(q, ldq, B, Nq, H * hdp);
-  op.map_k = make_head_map(k, ldk, B, Nkv, H * hdp);
-  op.map_v = make_head_map(v, ldv, B, Nkv, H * hdp);
-  return op;
-}
-
-void attn_configure() {
+void attn_tmemp_configure() {
   static bool done = false;
   if (done) return;
-  configure_one<64, 2, 3>();
-  configure_one<128, 1, 2>();
-  configure_one<192, 1, 1>();
+  CFGPP_CHECK_CUDA(cudaFuncSetAttribute(attn_tmemp_kernel<64, 2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        ACfg<64, 2, 5>::SMEM_BYTES));
   done = true;
 }
 
-void run_attn_op(const AttnOp& op, cudaStream_t stream) {
-  // opt-in only: the P-through-TMEM candidate has not been validated on hardware yet (see attention_tmemp.cu)
-  static const bool tmem_p = [] {
-    const char* e = std::getenv("CFGPP_ATTN_TMEM_P");
-    return e != nullptr && e[0] == '1';
-  }();
-  if (tmem_p && op.hd_pad == 64) return run_attn_tmemp(op, stream);
-  attn_configure();
-  switch (op.hd_pad) {
-    case 64: return launch<64, 2, 3>(op, stream);
-    case 128: return launch<128, 1, 2>(op, stream);
-    case 192: return launch<192, 1, 1>(op, stream);
-    default: throw Error(-1, "unsupported padded head dim");
-  }
+void run_attn_tmemp(const AttnOp& op, cudaStream_t stream) {
+  attn_tmemp_configure();
+  CFGPP_REQUIRE(op.hd_pad == 64, "the TMEM-P candidate is instantiated for padded head dim 64 only");
+  launch<64, 2, 5>(op, stream);
 }
 
 }  // namespace cfgpp
