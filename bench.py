@@ -2,16 +2,21 @@
 
     python bench.py --gpus N --steps K --warmup W            # ours: hand-written sm_100a path behind the C ABI
     python bench.py --impl reference --gpus N --steps K ...  # reference arm: the repo's CPU eager path (oracle)
+    python bench.py --config {sdxl_b2,sd15_b4,sdxl_dpmpp_64,lightning_b8}   # the other BASELINE.json configs
 
-Metric (BASELINE.json): images/sec, device-timed, SDXL 1024x1024 NFE=50 ddim_cfg++ lambda=0.6, batch 2 per GPU
-(= configs[2]); N>1 shards independent prompts over ranks (weak scaling, no per-step collective, one NCCL broadcast
-of the UNet weights at init). One "step" = one full sampling trajectory of one batch (NFE fused UNet+CFG++ steps):
-from zT resident in HBM to the final latent z0t — text encoding and VAE decode stay on the reference path and are
-outside the metric.
+Default workload = BASELINE.json's metric config (configs[2]): images/sec, device-timed, SDXL 1024x1024 NFE=50
+ddim_cfg++ lambda=0.6, batch 2 per GPU. N>1 shards independent prompts over ranks (weak scaling, no per-step
+collective, one NCCL broadcast of the UNet weights at init). One "step" = one full sampling trajectory of one batch
+(NFE fused UNet+CFG++ steps): from zT resident in HBM to the final latent — text encoding and VAE decode stay on the
+reference path and are outside the metric.
+
+Order of work (so that a lost box loses as little as possible): device-timed leg -> e2e leg -> roofline -> the line
+so far goes to STDERR (and to gpurun_out/bench_partial.json) -> GPU eager baseline -> bounded CPU baseline -> the ONE
+JSON line on stdout.
 
 Synthetic data: no checkpoint / tokenizer exists offline, so weights are seeded synthetic under the diffusers key
-names (random-init of the real SDXL architecture, 2,567,463,684 params) and the conditioning tensors are seeded
-random embeddings of the real shapes.
+names (random-init of the real architectures: SDXL 2,567,463,684 params, SD v1.5 859,520,964) and the conditioning
+tensors are seeded random embeddings of the real shapes.
 """
 from __future__ import annotations
 
@@ -30,16 +35,31 @@ sys.path.insert(0, str(ROOT))
 
 import torch  # noqa: E402
 
-NFE = 50
-LAMBDA = 0.6
-BATCH = 2
-LATENT = 128
-METRIC = "images/sec (device-timed) SDXL 1024x1024 NFE=50 ddim_cfg++"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, mean over the 12 consecutive
-# gemm_kernel launches of a 1280-channel transformer block in one `ncu --set full` capture (cold L2: an upper bound;
-# it equals the algorithmic A + W + residual bytes, i.e. no re-reads) — profiles/r01_v3_ncu_full.md
-NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 33.45e6
-NCU_TRAFFIC_SOURCE = "ncu --set full, gpurun_out/prof_gemm.ncu-rep (round 1 v3), summarised in profiles/r01_v3_ncu_full.md"
+# ----------------------------------------------------------------------------------------------------------------
+# workloads = BASELINE.json configs[1..4] (configs[0] is the CPU plumbing case = the cpu_baseline leg)
+# ----------------------------------------------------------------------------------------------------------------
+WORKLOADS = {
+    "sdxl_b2": dict(family="sdxl", method="ddim_cfg++", nfe=50, lam=0.6, batch=2, latent=128,
+                    metric="images/sec (device-timed) SDXL 1024x1024 NFE=50 ddim_cfg++",
+                    workload="SDXL 1024x1024 ddim_cfg++ lambda=0.6 NFE=50 batch=2 per GPU (configs[2])"),
+    "sd15_b4": dict(family="sd15", method="ddim_cfg++", nfe=50, lam=0.6, batch=4, latent=64,
+                    metric="images/sec (device-timed) SDv1.5 512x512 NFE=50 ddim_cfg++",
+                    workload="SDv1.5 512x512 ddim_cfg++ lambda=0.6 NFE=50 batch=4 per GPU (configs[1])"),
+    "sdxl_dpmpp_64": dict(family="sdxl", method="dpm++_2m_cfgpp", nfe=25, lam=0.6, batch=8, latent=128,
+                          metric="images/sec (device-timed) SDXL 1024x1024 NFE=25 dpm++_2m_cfgpp",
+                          workload="SDXL 1024x1024 dpm++_2m_cfgpp lambda=0.6 NFE=25 (24 steps), 8 prompts per GPU "
+                                   "per trajectory = prompt-batch 64 over 8 GPUs (configs[3])"),
+    "lightning_b8": dict(family="sdxl_lightning", method="ddim_cfg++_lightning", nfe=4, lam=1.0, batch=8, latent=128,
+                         metric="images/sec (device-timed) SDXL-Lightning 1024x1024 NFE=4 ddim_cfg++_lightning",
+                         workload="SDXL-Lightning 1024x1024 ddim_cfg++_lightning lambda=1.0 NFE=4 batch=8 per GPU "
+                                  "(configs[4])"),
+}
+DEFAULT_WORKLOAD = "sdxl_b2"
+ROOFLINE_TRAFFIC_FILE = ROOT / "profiles" / "roofline_traffic.json"  # written by tools/summarize_profiles.py from ncu
+
+
+def log(msg):
+    print(f"[bench] {msg}", file=sys.stderr, flush=True)
 
 
 def measured_peaks():
@@ -48,6 +68,11 @@ def measured_peaks():
         d = json.loads(p.read_text())
         return {"tflops": d.get("bf16_tflops_sustained", 1445.3), "hbm": d.get("hbm_gbs", 6587.7), "source": "measured"}
     return {"tflops": 1400.0, "hbm": 6650.0, "source": "fallback"}
+
+
+def unet_config(family):
+    from cfgpp_b200 import config as C
+    return C.sd15_config() if family == "sd15" else C.sdxl_config()
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -107,17 +132,19 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # synthetic workload
 # ----------------------------------------------------------------------------------------------------------------
-def synthetic_conditioning(cfg, batch, seed, pin=True):
-    """Host-side (pinned) conditioning + zT for one batch, shapes of latent_sdxl.py:222-257 / :289."""
+def synthetic_conditioning(cfg, wl, seed, pin=True):
+    """Host-side (pinned) conditioning + zT for one batch, shapes of latent_sdxl.py:222-257 / :289. With
+    cfg_guidance in {0, 1} (Lightning) the reference passes the added conditions un-duplicated (:249-252)."""
+    batch, latent = wl["batch"], wl["latent"]
     g = torch.Generator(device="cpu").manual_seed(seed)
-    t = {
-        "uc": torch.randn(batch, 77, cfg.cross_attention_dim, generator=g).half(),
-        "c": torch.randn(batch, 77, cfg.cross_attention_dim, generator=g).half(),
-        "pooled": torch.randn(2 * batch, cfg.pooled_dim, generator=g).half(),
-        "time_ids": torch.tensor([[1024., 1024., 0., 0., 1024., 1024.]] * (2 * batch)).half(),
-    }
+    t = {"uc": torch.randn(batch, 77, cfg.cross_attention_dim, generator=g).half(),
+         "c": torch.randn(batch, 77, cfg.cross_attention_dim, generator=g).half()}
+    if cfg.addition_embed_type == "text_time":
+        rows = batch if wl["lam"] in (0.0, 1.0) else 2 * batch
+        t["pooled"] = torch.randn(rows, cfg.pooled_dim, generator=g).half()
+        t["time_ids"] = torch.tensor([[1024., 1024., 0., 0., 1024., 1024.]] * rows).half()
     g2 = torch.Generator(device="cpu").manual_seed(42 + seed)
-    t["zT"] = torch.randn(batch, 4, LATENT, LATENT, generator=g2)
+    t["zT"] = torch.randn(batch, 4, latent, latent, generator=g2)
     if pin and torch.cuda.is_available():
         t = {k: v.pin_memory() for k, v in t.items()}
     return t
@@ -127,88 +154,167 @@ def nbytes(*ts):
     return int(sum(x.numel() * x.element_size() for x in ts))
 
 
+def make_solver(wl, cfg, dev, sd):
+    ns = argparse.Namespace(num_sampling=wl["nfe"])
+    if wl["family"] == "sd15":
+        from cfgpp_b200.latent_diffusion import get_solver
+        return get_solver(wl["method"], solver_config=ns, device=dev, model_key="synthetic:1234", state_dict=sd)
+    from cfgpp_b200.latent_sdxl import get_solver
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # Lightning: "checkpoint not found; using seeded synthetic weights"
+        return get_solver(wl["method"], solver_config=ns, device=dev, state_dict=sd,
+                          **({} if wl["family"] == "sdxl_lightning" else {"model_key": "synthetic:1234"}))
+
+
+def solve(solver, wl, t):
+    """One trajectory through the reference-facing solver API (reverse_process of the registered --method)."""
+    side = 8 * wl["latent"]
+    if wl["family"] == "sd15":
+        return solver.reverse_process(t["uc"], t["c"], wl["lam"], t["zT"])
+    add = {"text_embeds": t["pooled"], "time_ids": t["time_ids"]}
+    return solver.reverse_process(t["uc"], t["c"], wl["lam"], add, (side, side), zT=t["zT"])
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # CPU baseline = the oracle ("repo's own CPU eager path"), bounded sample
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_reference_sample(sd_provider, max_seconds=150.0):
-    """Times ONE SDXL UNet sample-forward (batch 1 at 128x128 latent, fp32, all host threads) of the oracle and
-    extrapolates to images/sec: one image = NFE x 2 such forwards (uncond + cond). Bounded: a GEMM probe first
-    decides whether the full forward fits the time budget; if not, a 64x64-latent forward is timed and scaled by the
-    algorithmic FLOP ratio (stated in `sample`)."""
-    import dataclasses
-    from cfgpp_b200 import config as C
-    from oracle import unet as O
-    cores = len(os.sched_getaffinity(0))
-    torch.set_num_threads(cores)
-    cfg = C.sdxl_config()
-    ocfg = O.UNetConfig(**{f.name: getattr(cfg, f.name) for f in dataclasses.fields(O.UNetConfig)})
-    # throughput probe (fp32 GEMM shaped like the dominant FF layer)
-    a, b = torch.randn(1024, 5120), torch.randn(5120, 1280)
-    torch.mm(a, b)
-    t0 = time.perf_counter()
-    for _ in range(3):
+def _host_ram_gb():
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available / 2**30
+    except Exception:  # noqa: BLE001
+        avail = 64.0
+    try:
+        lim = Path("/sys/fs/cgroup/memory.max").read_text().strip()
+        if lim.isdigit():
+            avail = min(avail, int(lim) / 2**30)
+    except Exception:  # noqa: BLE001
+        pass
+    return avail
+
+
+def pick_threads():
+    """Thread count for the CPU leg: the affinity mask can be far larger than the CPU time the container really gets
+    (round 1: 128 visible cores ran a GEMM at 160 GFLOP/s), and oversubscribed threads make the oracle slower, so a
+    short fp32 GEMM probe picks the fastest of {all, 64, 32, 16, 8} threads. Returns (threads, probe GFLOP/s)."""
+    avail = len(os.sched_getaffinity(0))
+    a, b = torch.randn(2048, 5120), torch.randn(5120, 1280)
+    best = (avail, 0.0)
+    for nt in sorted({n for n in (avail, 64, 32, 16, 8) if n <= avail}, reverse=True):
+        torch.set_num_threads(nt)
         torch.mm(a, b)
-    gflops = 3 * 2 * 1024 * 5120 * 1280 / (time.perf_counter() - t0) / 1e9
-    full_flops = 6.7612e12
-    latent = LATENT if full_flops / (gflops * 1e9 * 0.6) < max_seconds else 64
-    sd = sd_provider()
-    m = O.build_unet(ocfg, sd, dtype=torch.float32, device="cpu")
-    del sd
-    g = torch.Generator().manual_seed(0)
-    x = torch.randn(1, 4, latent, latent, generator=g)
-    ctx = torch.randn(1, 77, cfg.cross_attention_dim, generator=g)
-    add = {"text_embeds": torch.randn(1, cfg.pooled_dim, generator=g),
-           "time_ids": torch.tensor([[1024., 1024., 0., 0., 1024., 1024.]])}
-    with torch.no_grad():
         t0 = time.perf_counter()
-        m(x, torch.tensor(501), ctx, add)
-        dt = time.perf_counter() - t0
-    if latent == LATENT:
-        t_fwd, how = dt, "1 SDXL UNet sample-forward (batch 1, 128x128 latent, fp32) = 1/100 of one image"
-    else:
-        # algorithmic FLOPs per sample-forward (SURVEY §8d): 6.7612 T at 128x128 of which self-attention 0.7516 T;
-        # at 64x64 convs / token GEMMs shrink 4x and self-attention 16x
-        f128 = 6.7612
-        f64 = (f128 - 0.7516) / 4 + 0.7516 / 16
-        t_fwd = dt * f128 / f64
-        how = ("1 SDXL UNet sample-forward at 64x64 latent scaled to 128x128 by algorithmic FLOPs "
-               "(the full-size forward would exceed the time budget) = 1/100 of one image")
-    value = 1.0 / (2 * NFE * t_fwd)
-    return {"value": value, "unit": "images/sec", "cores": cores, "kind": "port", "sample": how,
-            "seconds_per_unet_forward": t_fwd, "probe_gflops": gflops}
+        for _ in range(2):
+            torch.mm(a, b)
+        gf = 2 * 2 * 2048 * 5120 * 1280 / (time.perf_counter() - t0) / 1e9
+        if gf > best[1] * 1.1:   # prefer more threads unless fewer are clearly faster
+            best = (nt, gf)
+    torch.set_num_threads(best[0])
+    return best
+
+
+class CpuOracle:
+    """fp32 oracle UNet on the host cores (the reference's `pipe_dtype=torch.float32` CPU path). Built ONCE, straight
+    in fp32 on the CPU with a cheap deterministic fill (timing does not depend on the weight values; no state dict and
+    no second copy are ever held: SDXL = 10.3 GB, SD v1.5 = 3.4 GB of host RAM). Sample = one UNet sample-forward at a
+    reduced latent, scaled to the workload's latent by algorithmic FLOPs."""
+
+    def __init__(self, family):
+        import dataclasses
+        from oracle import unet as O
+        self.cores, self.probe_gflops = pick_threads()
+        if family != "sd15" and _host_ram_gb() < 20.0:
+            log("host RAM < 20 GB: CPU sample falls back to the SD v1.5 UNet")
+            family = "sd15"
+        self.family = family
+        self.cfg = unet_config(family)
+        ocfg = O.UNetConfig(**{f.name: getattr(self.cfg, f.name) for f in dataclasses.fields(O.UNetConfig)})
+        t0 = time.perf_counter()
+        with torch.device("meta"):
+            m = O.UNet2DConditionModel(ocfg)
+        m = m.to_empty(device="cpu")
+        with torch.no_grad():
+            for i, p in enumerate(m.parameters()):
+                p.fill_(0.02 if p.dim() > 1 else (1.0 if i % 2 == 0 else 0.0))
+        self.m = m.eval().requires_grad_(False)
+        self.build_s = time.perf_counter() - t0
+        # algorithmic FLOPs per sample-forward (SURVEY §8d) at the full latent, and their self-attention part
+        self.f_full, self.f_attn, self.full_latent = ((0.8032, 0.1225, 64) if family == "sd15"
+                                                      else (6.7612, 0.7516, 128))
+
+    def sample(self, latent):
+        """seconds of ONE sample-forward at the FULL latent, measured at `latent` and FLOP-scaled."""
+        cfg = self.cfg
+        g = torch.Generator().manual_seed(0)
+        x = torch.randn(1, 4, latent, latent, generator=g)
+        ctx = torch.randn(1, 77, cfg.cross_attention_dim, generator=g)
+        add = None
+        if cfg.addition_embed_type == "text_time":
+            add = {"text_embeds": torch.randn(1, cfg.pooled_dim, generator=g),
+                   "time_ids": torch.tensor([[1024., 1024., 0., 0., 1024., 1024.]])}
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            self.m(x, torch.tensor(501), ctx, add)
+            dt = time.perf_counter() - t0
+        r = self.full_latent // latent  # convs / token GEMMs shrink r^2, self-attention r^4
+        f_small = (self.f_full - self.f_attn) / r ** 2 + self.f_attn / r ** 4
+        return dt * self.f_full / f_small, dt
+
+
+def cpu_baseline(wl, max_samples=1):
+    """images/sec of the reference's CPU eager path for workload `wl`: one image = NFE' x 2 sample-forwards."""
+    fam = "sd15" if wl["family"] == "sd15" else "sdxl"
+    orc = CpuOracle(fam)
+    # full-size latent when the GEMM probe says one forward fits ~45 s; otherwise the half-size latent, FLOP-scaled
+    # (small latents run less efficiently, so the scaled figure, if anything, UNDER-states the CPU path's speed)
+    est_full = orc.f_full * 1e3 / max(0.5 * orc.probe_gflops, 1e-3)
+    latent = orc.full_latent if est_full <= 45.0 else orc.full_latent // 2
+    best, raw = None, None
+    for _ in range(max_samples):
+        t_full, dt = orc.sample(latent)
+        if best is None or t_full < best:
+            best, raw = t_full, dt
+    steps = wl["nfe"] - 1 if wl["method"].startswith("dpm++") else wl["nfe"]
+    scale = 1.0
+    if orc.family != fam:  # RAM fallback: SD v1.5 module timed, scaled to SDXL by algorithmic FLOPs
+        scale = 6.7612 / 0.8032
+    value = 1.0 / (2 * steps * best * scale)
+    how = (f"1 {orc.family.upper()} UNet sample-forward (batch 1, fp32, {orc.cores} threads) at {latent}x{latent} latent "
+           f"= {raw:.1f} s" + (f", scaled to {orc.full_latent}x{orc.full_latent} by algorithmic FLOPs = {best:.1f} s"
+                               if latent != orc.full_latent else "") +
+           f"; one image = {2 * steps} such forwards" + ("; SD v1.5 module scaled to SDXL FLOPs (host RAM)" if scale != 1 else ""))
+    res = {"value": value, "unit": "images/sec", "cores": orc.cores, "cores_visible": len(os.sched_getaffinity(0)),
+           "kind": "port", "sample": how, "seconds_per_unet_forward": best * scale, "sample_seconds": raw,
+           "probe_gflops": orc.probe_gflops}
+    del orc
+    return res
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def run_reference_arm(args):
+def run_reference_arm(args, wl):
     """--impl reference: the reference's own CPU implementation of the path = the oracle port (the reference itself
-    cannot be imported: diffusers is absent and not installable offline), all host threads, bounded sample."""
+    cannot be imported: diffusers is absent and not installable offline), all host threads, bounded samples."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from cfgpp_b200 import config as C, weights as Wt
-    cfg = C.sdxl_config()
-    vals = []
-    for _ in range(max(1, min(args.steps, 2))):  # each "step" is one bounded sample; keep the run to a few minutes
-        r = cpu_reference_sample(lambda: Wt.synthetic_state_dict(cfg, seed=1234, device="cpu", dtype=torch.float16))
-        vals.append(r)
-    best = max(vals, key=lambda r: r["value"])
-    line = {"impl": "reference", "metric": METRIC, "value": best["value"], "unit": "images/sec", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * BATCH / best["value"],
+    r = cpu_baseline(wl, max_samples=max(1, min(args.steps, 2)))
+    line = {"impl": "reference", "metric": wl["metric"], "value": r["value"], "unit": "images/sec", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wl["batch"] / r["value"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "SDXL 1024x1024 ddim_cfg++ lambda=0.6 NFE=50 batch=2 (configs[2])",
-                       "global_batch": BATCH * args.gpus, "parallelism": f"dp{args.gpus}"},
-            "cpu_baseline": best,
-            "e2e": {"value": best["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "config": {"workload": wl["workload"], "global_batch": wl["batch"] * args.gpus,
+                       "parallelism": f"dp{args.gpus}"},
+            "cpu_baseline": r,
+            "e2e": {"value": r["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def run_ours(args):
+def run_ours(args, wl):
     import torch.distributed as dist
-    from cfgpp_b200 import config as C, schedule as S, weights as Wt
+    from cfgpp_b200 import weights as Wt
     from cfgpp_b200 import dist as D
     from cfgpp_b200.engine import NativeUNet
-    from cfgpp_b200.latent_sdxl import get_solver
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -223,41 +329,33 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg = C.sdxl_config()
+    cfg = unet_config(wl["family"])
+    NFE, BATCH, LATENT = wl["nfe"], wl["batch"], wl["latent"]
+    nsteps = NFE - 1 if wl["method"].startswith("dpm++") else NFE
     # ---- weights: rank 0 generates, ONE bucketed NCCL broadcast at init makes replicas bit-identical -------------
     sd = Wt.synthetic_state_dict(cfg, seed=1234, device=dev) if rank == 0 else None
     if world > 1:
         sd = D.broadcast_state_dict(sd, Wt.unet_param_specs(cfg), dev, src=0)
-    solver = get_solver("ddim_cfg++", solver_config=argparse.Namespace(num_sampling=NFE), device=dev,
-                        model_key="synthetic:1234", state_dict=sd)
+    solver = make_solver(wl, cfg, dev, sd)
     eng: NativeUNet = solver.unet
     eng.prepare(BATCH, LATENT, LATENT)
-    steps = S.ddim_cfgpp_steps(S.Schedule.make(NFE), LAMBDA, sdxl_indexing=True)
+    stats = eng.plan_stats
 
     # every trajectory uses its own prompt / zT (rank r owns items r, r+W, ...: D.shard_indices)
     n_traj = args.warmup + args.steps
     items = D.shard_indices(world * n_traj, rank, world)
-    host = [synthetic_conditioning(cfg, BATCH, seed=it) for it in items]
+    host = [synthetic_conditioning(cfg, wl, seed=it) for it in items]
     dev_in = [{k: v.to(dev) for k, v in h.items()} for h in host]
     torch.cuda.synchronize()
 
     def trajectory_device(i):
-        """inputs already resident in HBM (the `value` leg)."""
-        d = dev_in[i]
-        eng.set_prompt(torch.cat([d["uc"], d["c"]]), d["pooled"], d["time_ids"].float())
-        eng.set_schedule(S.STEP_DDIM_CFGPP, torch.float32, steps)
-        eng.set_state(d["zT"])
-        eng.run_steps(0, NFE)
-        return eng.get_state(1)
+        """inputs already resident in HBM (the `value` leg); the result stays on the device."""
+        return solve(solver, wl, dev_in[i])
 
     def trajectory_e2e(i):
         """public solver API with HOST buffers: H2D of this step's inputs, D2H of the result (the `e2e` leg)."""
-        h = host[i]
-        uc, c = h["uc"].to(dev, non_blocking=True), h["c"].to(dev, non_blocking=True)
-        add = {"text_embeds": h["pooled"].to(dev, non_blocking=True), "time_ids": h["time_ids"].to(dev, non_blocking=True)}
-        zT = h["zT"].to(dev, non_blocking=True)
-        z0t = solver.reverse_process(uc, c, LAMBDA, add, (1024, 1024), zT=zT)
-        return z0t.cpu()
+        t = {k: v.to(dev, non_blocking=True) for k, v in host[i].items()}
+        return solve(solver, wl, t).cpu()
 
     def barrier():
         if world > 1:
@@ -296,10 +394,14 @@ def run_ours(args):
     value = imgs / (ms_dev / 1e3)
     e2e_val = imgs / (ms_e2e / 1e3)
     peaks = measured_peaks()
+    log(f"value {value:.4f} img/s, e2e {e2e_val:.4f} img/s")
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM / implicit-GEMM conv), measured live with CUDA events ----
     d = dev_in[0]
-    eng.set_prompt(torch.cat([d["uc"], d["c"]]), d["pooled"], d["time_ids"].float())
+    if "pooled" in d:
+        eng.set_prompt(torch.cat([d["uc"], d["c"]]), d["pooled"], d["time_ids"].float())
+    else:
+        eng.set_prompt(torch.cat([d["uc"], d["c"]]))
     eng.profile_forward(d["zT"], 501.0)
     prof = eng.profile_forward(d["zT"], 501.0)
     by_kind = {0: [0.0, 0.0, 0], 1: [0.0, 0.0, 0], 2: [0.0, 0.0, 0], 3: [0.0, 0.0, 0]}
@@ -312,9 +414,14 @@ def run_ours(args):
     gemm_n = by_kind[0][2] + by_kind[1][2]
     tot_ms = sum(v[1] for v in by_kind.values())
     achieved = gemm_fl / (gemm_ms / 1e3) / 1e12
+    traffic, traffic_src = None, "no ncu --set full capture of this workload is committed"
+    if ROOFLINE_TRAFFIC_FILE.exists():
+        tj = json.loads(ROOFLINE_TRAFFIC_FILE.read_text()).get(args.config)
+        if tj:
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
     roofline = {"bound": "tensor", "kernel": "gemm_kernel<BN,GEGLU,CL> (tcgen05 GEMM + implicit-GEMM conv3x3)",
                 "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH, "traffic_source": NCU_TRAFFIC_SOURCE,
+                "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peaks["source"] + " (bf16 sustained)",
                 "flops_per_launch": gemm_fl / max(gemm_n, 1), "launches_per_forward": gemm_n,
                 "avg_launch_us": 1e3 * gemm_ms / max(gemm_n, 1), "share_of_step": gemm_ms / tot_ms,
@@ -323,57 +430,94 @@ def run_ours(args):
                 "by_kind_tflops": {"linear_gemm": by_kind[0][0] / max(by_kind[0][1], 1e-9) / 1e9,
                                    "conv3x3": by_kind[1][0] / max(by_kind[1][1], 1e-9) / 1e9,
                                    "attention": by_kind[2][0] / max(by_kind[2][1], 1e-9) / 1e9}}
-    step_tflops = eng.forward_flops * NFE * args.steps * world / (ms_dev / 1e3) / 1e12 / world
+    # executed FLOPs: `step_flops` every step + `prompt_flops` once per trajectory; the reference-equivalent
+    # algorithmic figure charges the K/V projections to every step (diffusers recomputes them)
+    per_traj_exec = stats["step_flops"] * nsteps + stats["prompt_flops"]
+    per_traj_algo = eng.forward_flops * nsteps
+    sec = ms_dev / 1e3 / args.steps
+    launches = int((eng.launches_per_step * nsteps + stats["prompt_launches"]) * args.steps)
 
-    line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+    line = {"metric": wl["metric"], "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": "SDXL 1024x1024 ddim_cfg++ lambda=0.6 NFE=50 batch=2 per GPU (configs[2])",
+            "config": {"workload": wl["workload"], "name": args.config,
                        "global_batch": BATCH * world, "parallelism": f"dp{world} (independent prompts, no per-step collective)",
-                       "step": "one full NFE=50 trajectory of one batch (UNet uncond+cond + fused CFG++/DDIM update per step)",
-                       "l2": "inputs larger than L2 (5.1 GB fp16 weights streamed every UNet forward; 126 MB L2)"},
+                       "step": f"one full trajectory of one batch ({nsteps} fused UNet uncond+cond + CFG++/scheduler steps)",
+                       "l2": "inputs larger than L2 (fp16 weights streamed every UNet forward: 5.1 GB SDXL / 1.7 GB SD v1.5; 126 MB L2)"},
             "e2e": {"value": e2e_val, "unit": "images/sec",
-                    "h2d_bytes_per_step": nbytes(host[0]["uc"], host[0]["c"], host[0]["pooled"], host[0]["time_ids"],
-                                                 host[0]["zT"]),
-                    "d2h_bytes_per_step": BATCH * 4 * LATENT * LATENT * 4,
-                    "api": "cfgpp_b200.latent_sdxl.get_solver('ddim_cfg++').reverse_process(...) with pinned host inputs"},
-            "gpu_launches": int((eng.launches_per_step * NFE + 80) * args.steps),
+                    "h2d_bytes_per_step": nbytes(*host[0].values()),
+                    "d2h_bytes_per_step": BATCH * 4 * LATENT * LATENT * (2 if wl["method"].startswith("dpm++") else 4),
+                    "api": f"get_solver('{wl['method']}').reverse_process(...) with pinned host inputs, result .cpu()"},
+            "gpu_launches": launches,
             "clocks": clocks, "roofline": roofline,
-            "unet_tflops_per_gpu": step_tflops, "unet_frac_of_peak": step_tflops / peaks["tflops"],
-            "forward_tflop": eng.forward_flops / 1e12}
+            "unet_tflops_per_gpu": {"executed": per_traj_exec / sec / 1e12, "algorithmic": per_traj_algo / sec / 1e12},
+            "unet_frac_of_peak": per_traj_exec / sec / 1e12 / peaks["tflops"],
+            "forward_tflop": {"executed_per_step": stats["step_flops"] / 1e12,
+                              "once_per_prompt": stats["prompt_flops"] / 1e12,
+                              "algorithmic_per_step": eng.forward_flops / 1e12}}
 
+    def checkpoint_line():
+        s = json.dumps(line)
+        print("[bench partial] " + s, file=sys.stderr, flush=True)
+        try:
+            out = ROOT / "gpurun_out"
+            out.mkdir(exist_ok=True)
+            (out / "bench_partial.json").write_text(s + "\n")
+        except Exception:  # noqa: BLE001
+            pass
+
+    checkpoint_line()
     # ---- baselines measured beside it (rank 0, N=1 only) ---------------------------------------------------------
     if world == 1 and not args.no_baselines:
+        from cfgpp_b200.latent_sdxl import release_engines
         del solver, eng
+        release_engines()
         torch.cuda.empty_cache()
-        line["gpu_eager_baseline"] = gpu_eager_baseline(cfg, sd, dev)
-        line["speedup_vs_gpu_eager"] = value / line["gpu_eager_baseline"]["value"]
-        sd_cpu = {k: v.cpu() for k, v in sd.items()}
+        try:
+            line["gpu_eager_baseline"] = gpu_eager_baseline(cfg, wl, sd, dev)
+            line["speedup_vs_gpu_eager"] = value / line["gpu_eager_baseline"]["value"]
+        except Exception as e:  # noqa: BLE001 — a failing baseline must not cost the measured line
+            line["gpu_eager_baseline"] = {"error": repr(e)[:200]}
         del sd
         torch.cuda.empty_cache()
-        line["cpu_baseline"] = cpu_reference_sample(lambda: sd_cpu)
+        checkpoint_line()
+        try:
+            line["cpu_baseline"] = cpu_baseline(wl)
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"error": repr(e)[:200], "value": None, "unit": "images/sec",
+                                    "cores": len(os.sched_getaffinity(0)), "kind": "port", "sample": "failed"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def gpu_eager_baseline(cfg, sd, dev, n_time=6, n_warm=2):
+def gpu_eager_baseline(cfg, wl, sd, dev, n_time=6, n_warm=2):
     """The north-star comparator ("reference CUDA path" stand-in): the restated diffusers op sequence
     + the reference-style Python step loop (incl. its per-step host syncs) under torch.autocast('cuda', fp16) on the
-    same GPU and inputs. Times `n_time` steps after `n_warm` and scales to NFE (every step costs the same)."""
+    same GPU and inputs. Times `n_time` steps after `n_warm` and scales to the trajectory (every step costs the same)."""
     import dataclasses
     from oracle import samplers as OSm, schedule as OS, unet as O
     ocfg = O.UNetConfig(**{f.name: getattr(cfg, f.name) for f in dataclasses.fields(O.UNetConfig)})
     m = O.build_unet(ocfg, sd, dtype=torch.float16, device=dev)
-    h = synthetic_conditioning(cfg, BATCH, seed=0, pin=False)
+    h = synthetic_conditioning(cfg, wl, seed=0, pin=False)
     uc, c, zT = h["uc"].to(dev), h["c"].to(dev), h["zT"].to(dev)
-    add = {"text_embeds": h["pooled"].to(dev), "time_ids": h["time_ids"].to(dev)}
-    tb = OS.make_tables(NFE)
+    add = {"text_embeds": h["pooled"].to(dev), "time_ids": h["time_ids"].to(dev)} if "pooled" in h else None
+    kind = "lightning" if wl["family"] == "sdxl_lightning" else "ddim"
+    n_time = min(n_time, wl["nfe"] - n_warm) if wl["nfe"] > n_warm + 1 else 1
+    n_warm = min(n_warm, max(1, wl["nfe"] - n_time))
 
     def run(nsteps):
-        tb_n = dataclasses.replace(tb, timesteps=tb.timesteps[:nsteps])
+        tb = OS.make_tables(wl["nfe"], kind)
+        extra = 1 if wl["method"].startswith("dpm++") else 0   # the DPM++ loop runs len(timesteps) - 1 steps
+        tb = dataclasses.replace(tb, timesteps=tb.timesteps[:nsteps + extra])
         with torch.autocast("cuda", dtype=torch.float16):
-            return OSm.sdxl_ddim_cfgpp(m, tb_n, zT, uc, c, LAMBDA, add)
+            if wl["family"] == "sd15":
+                return OSm.sd15_ddim_cfgpp(m, tb, zT, uc, c, wl["lam"])
+            if wl["method"].startswith("dpm++"):
+                return OSm.sdxl_dpmpp_2m_cfgpp(m, tb, zT, uc, c, wl["lam"], add)
+            if wl["family"] == "sdxl_lightning":
+                return OSm.sdxl_ddim_cfgpp_lightning(m, tb, zT, uc, c, wl["lam"], add)
+            return OSm.sdxl_ddim_cfgpp(m, tb, zT, uc, c, wl["lam"], add)
 
     run(n_warm)
     torch.cuda.synchronize()
@@ -383,7 +527,8 @@ def gpu_eager_baseline(cfg, sd, dev, n_time=6, n_warm=2):
     e1.record()
     torch.cuda.synchronize()
     ms_step = e0.elapsed_time(e1) / n_time
-    return {"value": BATCH / (NFE * ms_step / 1e3), "unit": "images/sec", "ms_per_unet_step": ms_step,
+    nsteps = wl["nfe"] - 1 if wl["method"].startswith("dpm++") else wl["nfe"]
+    return {"value": wl["batch"] / (nsteps * ms_step / 1e3), "unit": "images/sec", "ms_per_unet_step": ms_step,
             "what": "restated diffusers UNet + reference step loop, torch eager, autocast fp16, same GPU"}
 
 
@@ -393,12 +538,14 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=str, default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-baselines", action="store_true", help="skip the GPU-eager and CPU baselines at N=1")
     args = ap.parse_args()
+    wl = WORKLOADS[args.config]
     if args.impl == "reference":
-        run_reference_arm(args)
+        run_reference_arm(args, wl)
     else:
-        run_ours(args)
+        run_ours(args, wl)
 
 
 if __name__ == "__main__":

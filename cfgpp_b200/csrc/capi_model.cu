@@ -50,6 +50,14 @@ CFGPP_API int cfgpp_launches_per_step(cfgpp_handle* h, int* n) {
   return guarded([&] { *n = h->unet.launches_per_step(); });
 }
 
+CFGPP_API int cfgpp_plan_stats(cfgpp_handle* h, double* step_flops, double* prompt_flops, int* prompt_launches) {
+  return guarded([&] {
+    if (step_flops) *step_flops = h->unet.forward_flops() - h->unet.prompt_flops();
+    if (prompt_flops) *prompt_flops = h->unet.prompt_flops();
+    if (prompt_launches) *prompt_launches = h->unet.prompt_launches();
+  });
+}
+
 CFGPP_API int cfgpp_set_prompt(cfgpp_handle* h, const void* ctx, int n_ctx, const void* pooled, const float* time_ids,
                                int add_rows, void* stream) {
   return guarded([&] {

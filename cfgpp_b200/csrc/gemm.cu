@@ -648,7 +648,7 @@ GemmOp make_conv3x3_op(const __half* x, int B, int H, int W, int Cin, const __ha
   GemmParams& p = op.p;
   CFGPP_REQUIRE(Cin % BK == 0, "conv3x3 Cin must be a multiple of 64");
   CFGPP_REQUIRE(Cout % 8 == 0, "conv3x3 Cout must be a multiple of 8");
-  CFGPP_REQUIRE((W & (W - 1)) == 0 && (H & (H - 1)) == 0 && W <= 128, "conv3x3 needs power-of-two H, W with W <= 128");
+  CFGPP_REQUIRE(conv3x3_geometry_supported(H, W), "conv3x3 needs power-of-two H, W with W <= 128");
   const int Wt = W;
   const int Ht = (BM / Wt) < H ? (BM / Wt) : H;
   const int Nt = BM / (Wt * Ht);

@@ -70,4 +70,9 @@ GemmOp make_conv3x3_op(const __half* x, int B, int H, int W, int Cin, const __ha
 
 void run_gemm_op(const GemmOp& op, cudaStream_t stream);
 
+// Geometry the implicit-GEMM A tile (a 4-D TMA box of whole image rows) can address: power-of-two H, W with W <= 128.
+inline bool conv3x3_geometry_supported(int H, int W) {
+  return H >= 1 && W >= 1 && (W & (W - 1)) == 0 && (H & (H - 1)) == 0 && W <= 128;
+}
+
 }  // namespace cfgpp

@@ -623,9 +623,22 @@ Unet::Act Unet::build_upsample(const std::string& prefix, Act x, int H, int W) {
 
 void Unet::prepare(int batch, int h_lat, int w_lat) {
   CFGPP_REQUIRE(finalized_, "call cfgpp_finalize_weights first");
+  // validate BEFORE anything is freed: a rejected shape must leave the previous plan usable
   CFGPP_REQUIRE(batch >= 1 && 2 * batch <= 16, "batch must be 1..8 (UNet batch 2*batch <= 16)");
+  {
+    const int down = 1 << (d_.num_levels - 1);
+    CFGPP_REQUIRE(h_lat >= down && w_lat >= down && h_lat % down == 0 && w_lat % down == 0,
+                  "latent H, W must be multiples of 2^(num_levels-1)");
+    for (int i = 0, h = h_lat, w = w_lat; i < d_.num_levels; ++i, h /= 2, w /= 2)
+      CFGPP_REQUIRE(conv3x3_geometry_supported(h, w),
+                    "conv3x3 tiler: unsupported level geometry " + std::to_string(h) + "x" + std::to_string(w));
+  }
   CFGPP_CHECK_CUDA(cudaSetDevice(device_));
   CFGPP_CHECK_CUDA(cudaDeviceSynchronize());
+  // from here on the old plan is gone: a throw below must not leave the handle looking prepared
+  prepared_ = false;
+  nsteps_ = 0;
+  graph_valid_ = false;
   // drop the previous plan / workspace
   for (void* p : act_allocs_) cudaFree(p);
   act_allocs_.clear();
@@ -864,14 +877,20 @@ void Unet::prepare(int batch, int h_lat, int w_lat) {
   for (auto* pl : {&branch_plan_[0], &branch_plan_[1], &tail_plan_})
     for (auto& s : *pl) { forward_flops_ += s.flops; launches_per_step_ += s.launches; }
   for (auto& s : prologue_plan_) launches_per_step_ += s.launches;
-  for (auto& s : prompt_plan_) forward_flops_ += s.flops;
+  prompt_flops_ = 0.0;
+  prompt_launches_ = 0;
+  for (auto& s : prompt_plan_) { prompt_flops_ += s.flops; prompt_launches_ += s.launches; }
+  forward_flops_ += prompt_flops_;
   const double px = static_cast<double>(NB_) * H_ * W_;
   forward_flops_ += 2.0 * px * (36.0 * C0 + 36.0 * C0);  // conv_in + conv_out
   forward_flops_ += 2.0 * NB_ * (static_cast<double>(C0) * TE + static_cast<double>(TE) * TE +
                                  static_cast<double>(temb_total_) * TE);
-  if (has_aug_)
-    forward_flops_ += 2.0 * NB_ * (static_cast<double>(d_.projection_class_embeddings_input_dim) * TE +
-                                   static_cast<double>(TE) * TE);
+  if (has_aug_) {  // the add-embedding MLP runs in the prompt plan
+    const double f = 2.0 * NB_ * (static_cast<double>(d_.projection_class_embeddings_input_dim) * TE +
+                                  static_cast<double>(TE) * TE);
+    forward_flops_ += f;
+    prompt_flops_ += f;
+  }
   CFGPP_CHECK_CUDA(cudaDeviceSynchronize());
   prepared_ = true;
 }

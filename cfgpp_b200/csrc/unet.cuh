@@ -44,6 +44,8 @@ class Unet {
   size_t workspace_bytes() const { return workspace_bytes_; }
   double forward_flops() const { return forward_flops_; }
   int launches_per_step() const { return launches_per_step_; }
+  double prompt_flops() const { return prompt_flops_; }
+  int prompt_launches() const { return prompt_launches_; }
 
   void set_prompt(const __half* ctx, int n_ctx, const __half* pooled, const float* time_ids, int add_rows,
                   cudaStream_t stream);
@@ -137,8 +139,8 @@ class Unet {
   float* bgn_partial_ = nullptr;
   __half* out_override_ = nullptr;
   std::vector<PlanStep> prompt_plan_;    // cross-attention K/V projections + add-embedding
-  double forward_flops_ = 0.0;
-  int launches_per_step_ = 0;
+  double forward_flops_ = 0.0, prompt_flops_ = 0.0;
+  int launches_per_step_ = 0, prompt_launches_ = 0;
 
   // scratch (sized as the max over all uses while building, allocated afterwards; closures hold Scratch*)
   std::map<std::string, std::unique_ptr<Scratch>> scratch_;

@@ -51,6 +51,7 @@ class NativeUNet:
         self.latent_hw = (0, 0)
         self._nsteps = 0
         self._state_dtype = torch.float32
+        self._bound = None  # strong references to the tensors of the bound prompt (see bind_prompt)
 
     def close(self):
         if self._h:
@@ -67,10 +68,12 @@ class NativeUNet:
     def prepare(self, batch: int, h_lat: int, w_lat: int):
         if (batch, (h_lat, w_lat)) == (self.batch, self.latent_hw):
             return
+        # a failing native prepare() leaves the handle unprepared: forget the old shape and the bound prompt first so
+        # that the next call re-plans instead of running on freed buffers
+        self.batch, self.latent_hw, self._nsteps, self._bound = 0, (0, 0), 0, None
         with torch.cuda.device(self.device):
             nv.check(self.lib.cfgpp_prepare(self._h, c_int(batch), c_int(h_lat), c_int(w_lat)))
         self.batch, self.latent_hw = batch, (h_lat, w_lat)
-        self._nsteps = 0
 
     @property
     def workspace_bytes(self) -> int:
@@ -90,6 +93,13 @@ class NativeUNet:
         nv.check(self.lib.cfgpp_launches_per_step(self._h, byref(n)))
         return n.value
 
+    @property
+    def plan_stats(self) -> dict:
+        """{'step_flops': executed per fused step, 'prompt_flops' / 'prompt_launches': once per set_prompt}."""
+        sf, pf, pl = c_double(), c_double(), c_int()
+        nv.check(self.lib.cfgpp_plan_stats(self._h, byref(sf), byref(pf), byref(pl)))
+        return {"step_flops": sf.value, "prompt_flops": pf.value, "prompt_launches": pl.value}
+
     # ---- conditioning ----------------------------------------------------------------------------------------
     def set_prompt(self, ctx: torch.Tensor, pooled: Optional[torch.Tensor] = None,
                    time_ids: Optional[torch.Tensor] = None):
@@ -108,6 +118,23 @@ class NativeUNet:
             nv.check(self.lib.cfgpp_set_prompt(self._h, nv.ptr(ctx), c_int(ctx.shape[1]), nv.ptr(pooled),
                                                ctypes.cast(nv.ptr(time_ids), POINTER(c_float)), c_int(add_rows),
                                                nv.stream_ptr()))
+
+        self._bound = None  # a raw set_prompt() invalidates whatever bind_prompt() cached
+
+    def bind_prompt(self, uc: torch.Tensor, c: torch.Tensor, pooled: Optional[torch.Tensor] = None,
+                    time_ids: Optional[torch.Tensor] = None, force: bool = False):
+        """set_prompt(cat([uc, c]), pooled, time_ids) unless exactly these tensor OBJECTS (identity + in-place version
+        counter) are already bound. The engine keeps strong references to them, so an address can never be recycled
+        for another prompt while it is the cache key; every solver sharing this engine sees the same truth. Trajectory
+        entry points pass force=True (one K/V projection per trajectory, like the reference's per-call text path);
+        the identity test only serves the per-step `predict_noise` seam of the k-diffusion / callback loops."""
+        cur = (uc, c, pooled, time_ids)
+        if not force and self._bound is not None:
+            ts, vers = self._bound
+            if all(a is b for a, b in zip(ts, cur)) and vers == tuple(None if t is None else t._version for t in cur):
+                return
+        self.set_prompt(torch.cat([uc, c], dim=0), pooled, None if time_ids is None else time_ids.float())
+        self._bound = (cur, tuple(None if t is None else t._version for t in cur))
 
     # ---- un-fused seam: predict_noise ------------------------------------------------------------------------
     def predict_noise(self, z: torch.Tensor, t: float, in_scale: float = 1.0):

@@ -65,7 +65,6 @@ class StableDiffusion(K.KDiffusionMixin):
         self.skip = self._sch.skip
         self.final_alpha_cumprod = self._sch.final_alpha_cumprod
         self.scheduler = _Scheduler(self._sch, device)
-        self._prompt_key = None
 
     def __call__(self, *args: Any, **kwargs: Any) -> Any:
         self.sample(*args, **kwargs)
@@ -88,15 +87,10 @@ class StableDiffusion(K.KDiffusionMixin):
     def decode(self, zt):
         return self.vae.decode(zt).float()
 
-    def _prepare(self, zt, uc, c):
+    def _prepare(self, zt, uc, c, force: bool = False):
         b, _, h, w = zt.shape
-        if (b, (h, w)) != (self.unet.batch, self.unet.latent_hw):
-            self.unet.prepare(b, h, w)
-            self._prompt_key = None
-        key = (uc.data_ptr(), c.data_ptr(), uc._version, c._version)
-        if key != self._prompt_key:
-            self.unet.set_prompt(torch.cat([uc, c], dim=0))
-            self._prompt_key = key
+        self.unet.prepare(b, h, w)
+        self.unet.bind_prompt(uc, c, force=force)
 
     def predict_noise(self, zt: torch.Tensor, t: torch.Tensor, uc: torch.Tensor, c: torch.Tensor):
         if uc is None or c is None:
@@ -106,7 +100,7 @@ class StableDiffusion(K.KDiffusionMixin):
         return self.unet.predict_noise(zt, float(t))
 
     def _run(self, method, steps, z_init, uc, c, callback_fn=None):
-        self._prepare(z_init, uc, c)
+        self._prepare(z_init, uc, c, force=True)  # every trajectory re-binds its prompt
         eng = self.unet
         eng.set_schedule(method, z_init.dtype, steps)
         eng.set_state(z_init)

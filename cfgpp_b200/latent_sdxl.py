@@ -73,11 +73,25 @@ def get_engine(model_key: str, cfg: UNetConfig, device, state_dict=None) -> Nati
         raise RuntimeError("cfgpp_b200 solvers run on CUDA (sm_100a) only — there is no CPU fallback on the product "
                            "path; the CPU eager baseline lives in oracle/ and bench.py")
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
-    key = (model_key, cfg.name, idx, id(state_dict) if state_dict is not None else None)
-    if key not in _ENGINES:
-        sd = state_dict if state_dict is not None else resolve_state_dict(model_key, cfg, torch.device("cuda", idx))
-        _ENGINES[key] = NativeUNet(cfg, sd, torch.device("cuda", idx))
-    return _ENGINES[key]
+    key = (model_key, cfg.name, idx)
+    ent = _ENGINES.get(key)
+    # an explicit state_dict is part of the identity: the entry keeps a strong reference to it and compares with `is`
+    # (an id() of a dead dict can be recycled by a different one)
+    if ent is not None and ent[1] is state_dict:
+        return ent[0]
+    # same key, other weights: the cache entry is replaced; the old engine (5 GB) is destroyed by NativeUNet.__del__
+    # as soon as the last solver holding it goes away
+    sd = state_dict if state_dict is not None else resolve_state_dict(model_key, cfg, torch.device("cuda", idx))
+    eng = NativeUNet(cfg, sd, torch.device("cuda", idx))
+    _ENGINES[key] = (eng, state_dict)
+    return eng
+
+
+def release_engines():
+    """Destroy every cached engine (packed weights + workspace) — the cache otherwise lives as long as the process."""
+    for eng, _ in _ENGINES.values():
+        eng.close()
+    _ENGINES.clear()
 
 
 class _Scheduler:
@@ -123,7 +137,6 @@ class SDXL(K.KDiffusionMixin):
         self.skip = self._sch.skip
         self.final_alpha_cumprod = self._sch.final_alpha_cumprod
         self.scheduler = _Scheduler(self._sch, device)
-        self._prompt_key = None
 
     def __call__(self, *args: Any, **kwargs: Any) -> Any:
         self.sample(*args, **kwargs)
@@ -163,24 +176,13 @@ class SDXL(K.KDiffusionMixin):
         return self.vae.decode(zt).float()
 
     # ---- the seam: batched (uncond + cond) UNet forward on the native backend -----------------------------------
-    def _bind_prompt(self, uc, c, added_cond_kwargs):
-        key = (uc.data_ptr(), c.data_ptr(), uc._version, c._version,
-               None if not added_cond_kwargs else added_cond_kwargs['text_embeds'].data_ptr())
-        if key == self._prompt_key:
-            return
-        ctx = torch.cat([uc, c], dim=0)
-        if self.cfg.addition_embed_type == "text_time":
-            self.unet.set_prompt(ctx, added_cond_kwargs['text_embeds'], added_cond_kwargs['time_ids'].float())
-        else:
-            self.unet.set_prompt(ctx)
-        self._prompt_key = key
-
-    def _prepare(self, zt, uc, c, added_cond_kwargs):
+    def _prepare(self, zt, uc, c, added_cond_kwargs, force: bool = False):
         b, _, h, w = zt.shape
-        if (b, (h, w)) != (self.unet.batch, self.unet.latent_hw):
-            self.unet.prepare(b, h, w)
-            self._prompt_key = None
-        self._bind_prompt(uc, c, added_cond_kwargs)
+        self.unet.prepare(b, h, w)
+        if self.cfg.addition_embed_type == "text_time":
+            self.unet.bind_prompt(uc, c, added_cond_kwargs['text_embeds'], added_cond_kwargs['time_ids'], force=force)
+        else:
+            self.unet.bind_prompt(uc, c, force=force)
 
     def predict_noise(self, zt, t, uc, c, added_cond_kwargs, in_scale: float = 1.0):
         if uc is None or c is None:
@@ -289,7 +291,7 @@ class SDXL(K.KDiffusionMixin):
     # ---- shared trajectory driver -------------------------------------------------------------------------------
     def _run_trajectory(self, method, state_dtype, steps, z_init, uc, c, add_cond_kwargs, callback_fn, result):
         """`result`: 'z0t' (DDIM family returns the Tweedie estimate of the last step) or 'zt' (DPM++ returns x)."""
-        self._prepare(z_init, uc, c, add_cond_kwargs)
+        self._prepare(z_init, uc, c, add_cond_kwargs, force=True)  # every trajectory re-binds its prompt
         eng = self.unet
         eng.set_schedule(method, state_dtype, steps)
         eng.set_state(z_init)

@@ -97,6 +97,11 @@ int cfgpp_workspace_bytes(cfgpp_handle* h, size_t* bytes);
  * and the number of kernel launches one fused step enqueues. */
 int cfgpp_forward_flops(cfgpp_handle* h, double* flops);
 int cfgpp_launches_per_step(cfgpp_handle* h, int* n);
+/* Accounting of the prepared plan, all per 2*batch UNet forward: step_flops = FLOPs the fused step EXECUTES every step
+ * (excludes what runs once per prompt); prompt_flops / prompt_launches = the once-per-set_prompt part (cross-attention
+ * K/V projections, SDXL add-embedding). cfgpp_forward_flops == step_flops + prompt_flops is the reference-equivalent
+ * algorithmic figure (diffusers recomputes the K/V projections every step). */
+int cfgpp_plan_stats(cfgpp_handle* h, double* step_flops, double* prompt_flops, int* prompt_launches);
 
 /* ---- per-prompt conditioning: the tensors predict_noise concatenates (latent_sdxl.py:178-182, 249-257) ------ */
 /* ctx_dev: (2*batch, 77, cross_dim) fp16 = cat([uc, c]); pooled_dev: (add_rows, pooled_dim) fp16;

@@ -1,6 +1,8 @@
 """Kernel-level parity (through the C ABI) against torch fp32 references of the same op, with the reference's
 rounding points (fp16(acc+bias) then fp16 add of the residual / time embedding, fp32 norms rounded once).
-Tolerance: rel-L2 <= 2e-3 (observed ~3e-5 for GEMM/conv, 2.5e-4 for attention whose P is rounded to fp16)."""
+Gates are ~5x the error observed on B200 (printed by every test; `pytest -s` shows them): GEMM / conv observe ~3e-5
+(both sides round the same fp32 sum to fp16, so only accumulation-order flips of the last bit remain) -> 2e-4;
+attention observes ~2.5e-4 (P is rounded to fp16 before PV) -> 1.5e-3; norms observe <1e-4 -> 3e-4."""
 import pytest
 import torch
 
@@ -14,6 +16,15 @@ dev = torch.device("cuda:0")
 def _fp32_refs():
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+
+
+TOL_GEMM, TOL_ATTN, TOL_NORM = 2e-4, 1.5e-3, 3e-4
+
+
+def gate(what, got, ref, tol):
+    e = rel_l2(got, ref)
+    print(f"[kernel parity] {what}: rel-L2 {e:.3e} (gate {tol:.1e})")
+    assert e < tol, f"{what}: rel-L2 {e:.3e} >= {tol:.1e}"
 
 
 def rnd(g, *s, scale=1.0, shift=0.0):
@@ -44,7 +55,7 @@ def test_linear(M, N, K, hb, ha, bn):
     bias = rnd(g, N) if hb else None
     addend = rnd(g, M, N) if ha == 1 else (rnd(g, (M + ha - 1) // ha, N) if ha > 1 else None)
     out = nv.op_linear(a, w, bias, addend, ha if ha > 1 else 1, force_bn=bn)
-    assert rel_l2(out, ref_linear(a, w, bias, addend, ha)) < 2e-3
+    gate(f'linear {M}x{N}x{K}', out, ref_linear(a, w, bias, addend, ha), TOL_GEMM)
 
 
 def test_linear_dual_source_and_geglu():
@@ -53,7 +64,7 @@ def test_linear_dual_source_and_geglu():
     a1, a2 = rnd(g, 1024, 640), rnd(g, 1024, 320)
     w, bias = rnd(g, 320, 960, scale=960 ** -0.5), rnd(g, 320)
     out = nv.op_linear(a1, w, bias, None, 1, a2=a2)
-    assert rel_l2(out, ref_linear(torch.cat([a1, a2], 1), w, bias, None, 1)) < 2e-3
+    gate('linear dual-source', out, ref_linear(torch.cat([a1, a2], 1), w, bias, None, 1), TOL_GEMM)
     M, Cc = 512, 640
     inner = 4 * Cc
     a, w, b = rnd(g, M, Cc), rnd(g, 2 * inner, Cc, scale=Cc ** -0.5), rnd(g, 2 * inner)
@@ -64,7 +75,7 @@ def test_linear_dual_source_and_geglu():
     out = nv.op_linear(a, w[idx].contiguous(), b[idx].contiguous(), geglu=True)
     h = (a.float() @ w.float().t() + b.float()).half()
     ref = (h[:, :inner].float() * torch.nn.functional.gelu(h[:, inner:].float()).half().float()).half()
-    assert rel_l2(out, ref) < 2e-3
+    gate('geglu', out, ref, TOL_GEMM)
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,ht,hr", [
@@ -88,10 +99,10 @@ def test_conv3x3(B, H, W, Cin, Cout, ht, hr):
         ref = (ref.float() + addend.float().repeat_interleave(H * W, 0)).half()
     elif hr:
         ref = (ref.float() + addend.float()).half()
-    assert rel_l2(out, ref) < 2e-3
+    gate(f'conv3x3 {B}x{H}x{W} {Cin}->{Cout}', out, ref, TOL_GEMM)
     edge = torch.zeros(B, H, W, dtype=torch.bool, device=dev)
     edge[:, 0], edge[:, -1], edge[:, :, 0], edge[:, :, -1] = True, True, True, True
-    assert rel_l2(out[edge.reshape(-1)], ref[edge.reshape(-1)]) < 2e-3
+    gate('conv3x3 edge pixels', out[edge.reshape(-1)], ref[edge.reshape(-1)], TOL_GEMM)
 
 
 @pytest.mark.parametrize("B,H,Nq,Nkv", [(1, 1, 128, 128), (1, 4, 64, 64), (2, 5, 1024, 1024), (1, 10, 4096, 4096),
@@ -109,7 +120,7 @@ def test_attention(B, H, Nq, Nkv):
     out = nv.op_attention(q, k, v, H)
     qf, kf, vf = (t.float().reshape(B, -1, H, 64).transpose(1, 2) for t in (q, k, v))
     ref = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B, Nq, Cc)
-    assert rel_l2(out, ref) < 3e-3
+    gate(f'attention B{B} H{H} {Nq}x{Nkv}', out, ref, TOL_ATTN)
 
 
 @pytest.mark.parametrize("B,H,Nq,Nkv,hd", [(2, 8, 1024, 1024, 80), (1, 8, 4096, 4096, 40), (2, 8, 256, 256, 160),
@@ -129,7 +140,7 @@ def test_attention_padded_heads(B, H, Nq, Nkv, hd):
     out = nv.op_attention(q, k, v, H, head_dim=hd).reshape(B, Nq, H, P)
     qf, kf, vf = (t.float().reshape(B, -1, H, P)[..., :hd].transpose(1, 2) for t in (q, k, v))
     ref = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2)
-    assert rel_l2(out[..., :hd], ref) < 3e-3
+    gate(f'attention hd{hd} {Nq}x{Nkv}', out[..., :hd], ref, TOL_ATTN)
     assert out[..., hd:].abs().max() == 0
 
 
@@ -148,7 +159,7 @@ def test_groupnorm(B, HW, C1, C2, silu, eps):
                                          beta.float(), eps)
     if silu:
         ref = torch.nn.functional.silu(ref)
-    assert rel_l2(out, ref.reshape(B, Cc, HW).permute(0, 2, 1).half()) < 1e-3
+    gate(f'groupnorm {HW}x{Cc}', out, ref.reshape(B, Cc, HW).permute(0, 2, 1).half(), TOL_NORM)
 
 
 @pytest.mark.parametrize("M,Cc", [(4096, 1280), (16384, 640), (300, 128)])
@@ -157,4 +168,4 @@ def test_layernorm(M, Cc):
     g = torch.Generator().manual_seed(M)
     x, gamma, beta = rnd(g, M, Cc, scale=3.0, shift=1.0), rnd(g, Cc, scale=0.2, shift=1.0), rnd(g, Cc, scale=0.2)
     ref = torch.nn.functional.layer_norm(x.float(), (Cc,), gamma.float(), beta.float(), 1e-5).half()
-    assert rel_l2(nv.op_layernorm(x, gamma, beta), ref) < 1e-3
+    gate(f'layernorm {M}x{Cc}', nv.op_layernorm(x, gamma, beta), ref, TOL_NORM)
