@@ -502,6 +502,9 @@ def gpu_eager_baseline(cfg, wl, sd, dev, n_time=6, n_warm=2):
     h = synthetic_conditioning(cfg, wl, seed=0, pin=False)
     uc, c, zT = h["uc"].to(dev), h["c"].to(dev), h["zT"].to(dev)
     add = {"text_embeds": h["pooled"].to(dev), "time_ids": h["time_ids"].to(dev)} if "pooled" in h else None
+    if add is not None and add["text_embeds"].shape[0] == wl["batch"] and wl["batch"] > 1:
+        # un-duplicated added conditions (cfg_guidance == 1) only broadcast for ONE image in diffusers: duplicate
+        add = {k: torch.cat([v, v]) for k, v in add.items()}
     kind = "lightning" if wl["family"] == "sdxl_lightning" else "ddim"
     n_time = min(n_time, wl["nfe"] - n_warm) if wl["nfe"] > n_warm + 1 else 1
     n_warm = min(n_warm, max(1, wl["nfe"] - n_time))

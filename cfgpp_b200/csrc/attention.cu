@@ -17,6 +17,7 @@
 //                   and p <= 256 stays well inside fp16 / fp32 range.
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "attention.cuh"
 #include "common.cuh"
@@ -24,7 +25,10 @@
 namespace cfgpp {
 
 void attn_configure();
-void run_attn_tmemp(const AttnOp& op, cudaStream_t stream);  // attention_tmemp.cu (round-2 candidate, opt-in)
+// attention_cross.cu: single-KV-tile (cross-attention) kernel
+void xattn_configure();
+bool xattn_applicable(const AttnOp& op);
+void run_xattn_op(const AttnOp& op, cudaStream_t stream);
 
 namespace {
 
@@ -369,16 +373,19 @@ void attn_configure() {
   configure_one<64, 2, 3>();
   configure_one<128, 1, 2>();
   configure_one<192, 1, 1>();
+  xattn_configure();
   done = true;
 }
 
 void run_attn_op(const AttnOp& op, cudaStream_t stream) {
-  // opt-in only: the P-through-TMEM candidate has not been validated on hardware yet (see attention_tmemp.cu)
-  static const bool tmem_p = [] {
-    const char* e = std::getenv("CFGPP_ATTN_TMEM_P");
+  attn_configure();
+  // Nkv <= 128 (the 77 text tokens): K / V resident, query tiles streamed (attention_cross.cu). CFGPP_NO_XATTN=1 keeps
+  // the general flash kernel for A/B runs.
+  static const bool no_x = [] {
+    const char* e = std::getenv("CFGPP_NO_XATTN");
     return e != nullptr && e[0] == '1';
   }();
-  if (tmem_p && op.hd_pad == 64) return run_attn_tmemp(op, stream);
+  if (!no_x && xattn_applicable(op)) return run_xattn_op(op, stream);
   attn_configure();
   switch (op.hd_pad) {
     case 64: return launch<64, 2, 3>(op, stream);

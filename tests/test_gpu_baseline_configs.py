@@ -73,7 +73,11 @@ def test_lightning_nfe4_trajectory_vs_oracle():
     z, uc, c, add = make_inputs(cfg, B, hw, dev, duplicate_added=False)
     tb = OS.make_tables(nfe, "lightning")
     rec = []
-    z0_ref = OSm.sdxl_ddim_cfgpp_lightning(ref, tb, z, uc, c, lam, add, record=rec)
+    # The reference passes (1, .) added conditions at cfg_guidance == 1 and lets them broadcast over the UNet batch of
+    # 2; that only works for ONE image. The engine generalises it to `batch` rows (row r of either half uses row
+    # r % batch); the oracle is given the equivalent duplicated form.
+    dup = lambda a: {k: torch.cat([v, v]) for k, v in a.items()}  # noqa: E731
+    z0_ref = OSm.sdxl_ddim_cfgpp_lightning(ref, tb, z, uc, c, lam, dup(add), record=rec)
     steps = S.ddim_cfgpp_steps(S.Schedule.make(nfe, "lightning"), lam, sdxl_indexing=True, tables_on_device=True)
     assert [int(s.t) for s in steps] == [int(t) for t in tb.timesteps]
     net.prepare(B, hw, hw)
@@ -98,7 +102,7 @@ def test_lightning_nfe4_trajectory_vs_oracle():
         lt = LX.get_solver("ddim_cfg++_lightning", solver_config=SimpleNamespace(num_sampling=nfe), device=dev,
                            unet_config=cfg, state_dict=sd)
     got = lt.reverse_process(uc8, c8, 1.0, add8, shape=(8 * hw, 8 * hw), zT=z8)
-    want = OSm.sdxl_ddim_cfgpp_lightning(ref, tb, z8, uc8, c8, 1.0, add8)
+    want = OSm.sdxl_ddim_cfgpp_lightning(ref, tb, z8, uc8, c8, 1.0, dup(add8))
     e8 = rel_l2(got, want)
     print(f"lightning solver batch 8: rel-L2 final z0t {e8:.3e}")
     assert got.shape == (8, 4, hw, hw) and e8 <= 3e-2
