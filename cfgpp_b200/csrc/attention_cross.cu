@@ -286,7 +286,10 @@ void xattn_configure() {
   cfg(xattn_kernel<192, 1, 128>, XCfg<192, 1>::SMEM_BYTES);
 }
 
-bool xattn_applicable(const AttnOp& op) { return op.p.Nkv <= 128 && op.p.Nq >= 2 * BQ; }
+// (head dim 192 at two query tiles measured slower than the flash kernel: one CTA per SM and a single-stage Q ring)
+bool xattn_applicable(const AttnOp& op) {
+  return op.p.Nkv <= 128 && op.p.Nq >= (op.hd_pad == 192 ? 4 : 2) * BQ;
+}
 
 void run_xattn_op(const AttnOp& op, cudaStream_t stream) {
   const bool narrow = op.p.Nkv <= 80;

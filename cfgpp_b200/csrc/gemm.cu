@@ -33,6 +33,8 @@ constexpr int kProducerWarp = 8;
 constexpr int kMmaWarp = 9;
 constexpr int kAllocWarp = 10;
 constexpr int A_BYTES = BM * BK * 2;
+constexpr int kSkMaxClusters = 256;            // stream-K: flags[c] arrivals, flags[kSkDoneOffset + c] consumers
+constexpr int kSkDoneOffset = kSkMaxClusters;
 
 template <int BN, bool GEGLU, int CL = 1>
 struct Cfg {
@@ -140,12 +142,82 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
   auto tile_m_blk = [&](int tile) { return (tile % num_mg) * CL + cta_rank; };
   auto tile_n_blk = [&](int tile) { return tile / num_mg; };
 
+  // ---- work schedule: "stream-K for the remainder" -------------------------------------------------------------
+  // D = the tiles that fill whole rounds over the clusters are walked data-parallel (tile = cluster + r * clusters);
+  // the R = T mod clusters left-over tiles would cost a full extra round with most clusters idle, so their
+  // R * nkb k-blocks are split evenly over ALL clusters instead: cluster c owns the contiguous unit range
+  // [c U / P, (c + 1) U / P) of the linearised (tile, k-block) space — at most two pieces, of two adjacent tiles. The
+  // piece that contains a tile's LAST k-block finishes the tile: it adds the fp32 partial accumulators the other
+  // pieces parked in the workspace (fixed order: deterministic) and runs the normal epilogue. Stream-K items come
+  // first, the non-finishing piece ahead of the finishing one, so that partials are published early and the fix-up
+  // epilogue overlaps the following data-parallel main loops. All clusters of the grid are co-resident (grid <= SMs,
+  // one CTA per SM; a dependent grid is only scheduled after every CTA of this one has started), so the spin-wait
+  // on a peer's flag cannot deadlock.
+  constexpr int kItemFull = 0, kItemPart = 1, kItemFin = 2;
+  struct Item {
+    int tile, kb0, kb1, kind, c_first;
+  };
+  int sk_r = 0;  // R
+  long sk_units = 0;
+  if (p.sk_ws != nullptr && num_tiles % num_clusters != 0) {
+    sk_r = num_tiles % num_clusters;
+    sk_units = static_cast<long>(sk_r) * nkb;
+  }
+  const int dp_tiles = num_tiles - sk_r;
+  auto sk_u0 = [&](int c) { return static_cast<int>(sk_units * c / num_clusters); };
+  Item sk_item[2];
+  int n_sk = 0;
+  if (sk_r > 0) {
+    const int u0 = sk_u0(cluster_id), u1 = sk_u0(cluster_id + 1);
+    if (u1 > u0) {
+      const int s0 = u0 / nkb;
+      const int e0 = (u1 < (s0 + 1) * nkb) ? u1 : (s0 + 1) * nkb;
+      auto make = [&](int s, int b, int e) {  // units [b, e) of stream-K tile s
+        Item it;
+        it.tile = dp_tiles + s;
+        it.kb0 = b - s * nkb;
+        it.kb1 = e - s * nkb;
+        it.c_first = cluster_id;
+        if (it.kb1 < nkb) {
+          it.kind = kItemPart;
+        } else if (it.kb0 == 0) {
+          it.kind = kItemFull;
+        } else {
+          it.kind = kItemFin;
+          int c = cluster_id;
+          while (c > 0 && sk_u0(c) > s * nkb) --c;  // the cluster whose range holds the tile's first k-block
+          it.c_first = c;
+        }
+        return it;
+      };
+      if (u1 > e0) sk_item[n_sk++] = make(s0 + 1, e0, u1);  // head of the next tile: never finishing, goes first
+      sk_item[n_sk++] = make(s0, u0, e0);
+    }
+  }
+  const int n_dp = (dp_tiles > cluster_id) ? (dp_tiles - cluster_id + num_clusters - 1) / num_clusters : 0;
+  const int n_items = n_sk + n_dp;
+  auto item_at = [&](int i) {
+    if (i < n_sk) return sk_item[i];
+    Item it;
+    it.tile = cluster_id + (i - n_sk) * num_clusters;
+    it.kb0 = 0;
+    it.kb1 = nkb;
+    it.kind = kItemFull;
+    it.c_first = cluster_id;
+    return it;
+  };
+  constexpr unsigned kSkArrivals = CL * kEpiWarps;  // warps that publish / consume one cluster's partial
+  // partial accumulator of (cluster c, CTA rank r): [BN / 32 column chunks][128 rows][32] fp32
+  auto sk_ws = [&](int c) { return p.sk_ws + (static_cast<size_t>(c) * CL + cta_rank) * (static_cast<size_t>(BM) * BN); };
+
   if (warp_idx == kProducerWarp) {
     {
       // ===================== TMA producer (whole warp walks the loop, one elected lane issues) ============
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int item_i = 0; item_i < n_items; ++item_i) {
+        const Item item = item_at(item_i);
+        const int tile = item.tile;
         const int m_blk = tile_m_blk(tile);
         const int n_blk = tile_n_blk(tile);
         const int m0 = m_blk * BM;
@@ -157,14 +229,14 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
           h0 = r / p.W;
           w0 = r - h0 * p.W;
         }
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = item.kb0; kb < item.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           if (!elect_one()) {
             // non-elected lanes only keep the loop state in step
           } else if constexpr (CL == 1) {
-            if (tile == cluster_id && kb == 0) TL(3);
+            if (item_i == 0 && kb == item.kb0) TL(3);
             mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
             if (p.conv) {
               const int tap = kb / p.cpb;
@@ -180,7 +252,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
             }
             tma_load_2d(sb, &map_b, &full_bar[stage], kb * BK, n_blk * BN);
           } else {
-            if (tile == cluster_id && kb == 0) TL(3);
+            if (item_i == 0 && kb == item.kb0) TL(3);
             // both CTAs fill their own smem; all bytes are accounted on the leader's barrier (the MMA issuer's)
             if (is_leader_cta) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
             if (p.conv) {
@@ -210,14 +282,15 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
       constexpr uint32_t idesc = make_idesc_f16(BM * CL, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      for (int it = 0; it < n_items; ++it) {
+        const Item item = item_at(it);
+        const int kb_first = item.kb0, kb_last = item.kb1 - 1;
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&tmem_empty_bar[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * C::ACC_STRIDE;
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = kb_first; kb <= kb_last; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
@@ -225,25 +298,25 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
           const uint64_t a_desc = make_sdesc_sw128(a_addr, 1024, 0);
           const uint64_t b_desc = make_sdesc_sw128(b_addr, 1024, 0);
           if (elect_one()) {
-            if (it == 0 && kb == 0) TL(4);
-            if (it == 0 && kb == nkb - 1) TL(5);
-            if (kb == nkb - 1) TL(6);
+            if (it == 0 && kb == kb_first) TL(4);
+            if (it == 0 && kb == kb_last) TL(5);
+            if (kb == kb_last) TL(6);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
               if constexpr (CL == 1)
-                umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb != kb_first || k != 0) ? 1u : 0u);
               else
-                umma_f16_cg2(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                umma_f16_cg2(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb != kb_first || k != 0) ? 1u : 0u);
             }
             // on retirement: free the smem slot (pair: in both CTAs) and, after the last k-block, publish the
             // accumulator
             if constexpr (CL == 1) {
               umma_commit(&empty_bar[stage]);
-              if (kb == nkb - 1) umma_commit(&tmem_full_bar[as]);
+              if (kb == kb_last) umma_commit(&tmem_full_bar[as]);
             } else {
               umma_commit_cg2(&empty_bar[stage]);
-              if (kb == nkb - 1) umma_commit_cg2(&tmem_full_bar[as]);
+              if (kb == kb_last) umma_commit_cg2(&tmem_full_bar[as]);
             }
           }
           if (++stage == C::STAGES) {
@@ -280,11 +353,69 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
         tma_load_2d(my_slab + j * C::EPI_SUB_BYTES, &map_res, my_res_bar, n_blk * C::OUT_N + j * 32,
                     m_blk * BM + q * 32);
     };
-    if (full_res && lane == 0 && cluster_id < num_tiles) issue_residual(cluster_id);
-    int it = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+    // residual tiles are prefetched one item ahead; stream-K pieces that only park a partial take none
+    auto next_res_item = [&](int from) {
+      int i = from;
+      while (i < n_items && item_at(i).kind == kItemPart) ++i;
+      return i;
+    };
+    if (full_res && lane == 0) {
+      const int i0 = next_res_item(0);
+      if (i0 < n_items) issue_residual(item_at(i0).tile);
+    }
+    int res_uses = 0;
+    for (int it = 0; it < n_items; ++it) {
+      const Item item = item_at(it);
+      const int tile = item.tile;
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
+      if (item.kind == kItemPart) {
+        // ---- stream-K piece that does not finish its tile: park the raw fp32 accumulator, publish, move on ----
+        mbar_wait(&tmem_full_bar[as], aph);
+        tc_fence_after();
+        const uint32_t t_base = tmem_base + as * C::ACC_STRIDE + lane_off;
+        float* ws = sk_ws(cluster_id);
+#pragma unroll 1
+        for (int jt = half; jt < BN / 32; jt += 2) {
+          uint32_t v[32];
+          tmem_ld_x32(t_base + jt * 32, v);
+          tmem_ld_wait();
+          float4* dst = reinterpret_cast<float4*>(ws + (static_cast<size_t>(jt) * BM + row) * 32);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            dst[e] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
+                                 __uint_as_float(v[4 * e + 3]));
+        }
+        tc_fence_before();
+        __threadfence();  // this lane's partial is visible device-wide before the warp's arrival is counted
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CL == 2)
+            mbar_arrive_leader(&tmem_empty_bar[as]);
+          else
+            mbar_arrive(&tmem_empty_bar[as]);
+          atomicAdd(p.sk_flags + cluster_id, 1u);
+        }
+        __syncwarp();
+        continue;
+      }
+      const bool fin = (item.kind == kItemFin);
+      auto contributes = [&](int c) { return sk_u0(c + 1) > sk_u0(c); };
+      // v[0..32) += the partials parked by the clusters that hold the earlier k-blocks of this tile (fixed order)
+      auto add_partials = [&](uint32_t (&v)[32], int jt) {
+        for (int c = item.c_first; c < cluster_id; ++c) {
+          if (!contributes(c)) continue;
+          const float4* src = reinterpret_cast<const float4*>(sk_ws(c) + (static_cast<size_t>(jt) * BM + row) * 32);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float4 f = __ldcg(src + e);
+            v[4 * e] = __float_as_uint(__uint_as_float(v[4 * e]) + f.x);
+            v[4 * e + 1] = __float_as_uint(__uint_as_float(v[4 * e + 1]) + f.y);
+            v[4 * e + 2] = __float_as_uint(__uint_as_float(v[4 * e + 2]) + f.z);
+            v[4 * e + 3] = __float_as_uint(__uint_as_float(v[4 * e + 3]) + f.w);
+          }
+        }
+      };
       const int m_blk = tile_m_blk(tile);
       const int n_blk = tile_n_blk(tile);
       const int m = m_blk * BM + row;
@@ -337,7 +468,17 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
       mbar_wait(&tmem_full_bar[as], aph);
       if (leader) { if (it == 0) TL(7); TL(9); if (tl) tl[12] = it + 1; }
       tc_fence_after();
-      if (full_res) mbar_wait(my_res_bar, it & 1);
+      if (full_res) mbar_wait(my_res_bar, (res_uses++) & 1);
+      if (fin) {  // every lane polls (acquire) until all warps of every contributing cluster have published
+        for (int c = item.c_first; c < cluster_id; ++c) {
+          if (!contributes(c)) continue;
+          unsigned seen;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.sk_flags + c) : "memory");
+            if (seen < kSkArrivals) __nanosleep(40);
+          } while (seen < kSkArrivals);
+        }
+      }
       if (leader && it == 0) TL(13);
       const uint32_t t_base = tmem_base + as * C::ACC_STRIDE + lane_off;
 
@@ -355,6 +496,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
             uint32_t v[32];
             tmem_ld_x32(t_base + j * 32, v);
             tmem_ld_wait();
+            if (fin) add_partials(v, j);
             const int n0 = n_blk * BN + j * 32;
             uint8_t* srow = my_row + j * C::EPI_SUB_BYTES;
 #pragma unroll
@@ -435,6 +577,10 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
             tmem_ld_x32(t_base + j * 32, va);
             tmem_ld_x32(t_base + BN / 2 + j * 32, vg);
             tmem_ld_wait();
+            if (fin) {
+              add_partials(va, j);
+              add_partials(vg, BN / 64 + j);
+            }
             uint8_t* srow = my_row + j * C::EPI_SUB_BYTES;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -504,8 +650,23 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
         tma_store_commit();
         if (leader) { if (it == 0) TL(8); TL(10); }
         tma_store_wait_read0();  // this warp's staging blocks have been read out: reusable
-        const int next = tile + num_clusters;
-        if (full_res && next < num_tiles) issue_residual(next);
+        if (full_res) {
+          const int nx = next_res_item(it + 1);
+          if (nx < n_items) issue_residual(item_at(nx).tile);
+        }
+        if (fin) {
+          // this warp has consumed the partials: the last of the kSkArrivals consumers re-arms the contributor's
+          // flag, so the buffers are back in their initial state when the kernel ends (CUDA-graph replays bake the
+          // arguments, an epoch counter is not an option)
+          for (int c = item.c_first; c < cluster_id; ++c) {
+            if (!contributes(c)) continue;
+            const unsigned old = atomicAdd(p.sk_flags + kSkDoneOffset + c, 1u);
+            if (old == kSkArrivals - 1) {
+              p.sk_flags[kSkDoneOffset + c] = 0u;
+              p.sk_flags[c] = 0u;
+            }
+          }
+        }
       }
       __syncwarp();
       // (written after the tmem_empty arrive: a global store ahead of that cluster-scope release would delay it)
@@ -557,6 +718,42 @@ bool cluster_disabled() {
   return v == 1;
 }
 
+// CFGPP_NO_STREAMK=1 switches the remainder stream-K off (A/B runs); it is also off when the two CFG halves run as
+// concurrent launch plans (CFGPP_SPLIT=1), because the partial-accumulator workspace is shared by all launches of a stream.
+bool streamk_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CFGPP_NO_STREAMK");
+    const char* sp = getenv("CFGPP_SPLIT");
+    v = ((e && e[0] == '1') || (sp && sp[0] == '1')) ? 0 : 1;
+  }
+  return v == 1;
+}
+double streamk_min_saved() {  // k-blocks of main loop the split must save per cluster (CFGPP_STREAMK_MIN overrides)
+  static double v = -1.0;
+  if (v < 0) {
+    const char* e = getenv("CFGPP_STREAMK_MIN");
+    v = e ? atof(e) : 3.0;
+  }
+  return v;
+}
+// One workspace per device: partial accumulators for up to 148 CTAs ([128 x 256] fp32 each) + the flag words.
+void streamk_buffers(float** ws, unsigned** flags) {
+  static float* g_ws[16] = {nullptr};
+  static unsigned* g_flags[16] = {nullptr};
+  int dev = 0;
+  CFGPP_CHECK_CUDA(cudaGetDevice(&dev));
+  CFGPP_REQUIRE(dev >= 0 && dev < 16, "device index out of range");
+  if (g_ws[dev] == nullptr) {
+    CFGPP_CHECK_CUDA(cudaMalloc(&g_ws[dev], static_cast<size_t>(kSkMaxClusters) * BM * 256 * sizeof(float)));
+    CFGPP_CHECK_CUDA(cudaMalloc(&g_flags[dev], 2 * kSkMaxClusters * sizeof(unsigned)));
+    CFGPP_CHECK_CUDA(cudaMemset(g_flags[dev], 0, 2 * kSkMaxClusters * sizeof(unsigned)));
+    CFGPP_CHECK_CUDA(cudaDeviceSynchronize());
+  }
+  *ws = g_ws[dev];
+  *flags = g_flags[dev];
+}
+
 // Tile-width heuristic, fitted to tools/bn_sweep.py (every GEMM / conv shape of the SDXL UNet x every width, timed
 // inside CUDA graphs): time ~ rounds x (BN + 50), rounds = tiles each CTA (pair) walks. The additive term is the
 // per-k-block cost that does not scale with the tile width (A-tile ingest, barrier round trip); 64-wide tiles never
@@ -605,6 +802,19 @@ void finish_op(GemmOp& op, const __half* w, int force_bn) {
   const int groups = ((p.num_m_blocks + op.cluster - 1) / op.cluster) * p.num_n_blocks;
   const int max_clusters = num_sms() / op.cluster;
   op.grid = op.cluster * (groups < max_clusters ? groups : max_clusters);
+  // stream-K for the remainder tiles (kernel comment "work schedule"): worth it when the left-over round would idle
+  // the clusters for at least a few k-blocks and the pieces are not slivers
+  p.sk_ws = nullptr;
+  p.sk_flags = nullptr;
+  const int rem = groups % max_clusters;
+  if (streamk_enabled() && rem != 0 && max_clusters <= kSkMaxClusters) {
+    const double piece = static_cast<double>(rem) * p.num_k_blocks / max_clusters;
+    const double saved = p.num_k_blocks - piece;
+    if (saved >= streamk_min_saved() && piece >= 2.0) {
+      op.grid = op.cluster * max_clusters;  // all clusters take part, also when there are fewer tiles than clusters
+      streamk_buffers(&p.sk_ws, &p.sk_flags);
+    }
+  }
 }
 
 }  // namespace

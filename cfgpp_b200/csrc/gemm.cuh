@@ -46,6 +46,9 @@ struct GemmParams {
   float ln_inv_c, ln_eps;
   const float* ln_s;       // [N] fp32
   const float* ln_t;       // [N] fp32
+  // ---- stream-K for the remainder tiles (see gemm.cu "work schedule"); null = plain data-parallel tile walk ------
+  float* sk_ws;            // per (cluster, CTA rank) partial accumulator [BN / 32][128][32] fp32
+  unsigned* sk_flags;      // [2 * 256] zero-initialised, self-resetting arrival / consumer counters
 };
 
 struct GemmOp {

@@ -2,7 +2,7 @@
 rounding points (fp16(acc+bias) then fp16 add of the residual / time embedding, fp32 norms rounded once).
 Gates are ~5x the error observed on B200 (printed by every test; `pytest -s` shows them): GEMM / conv observe ~3e-5
 (both sides round the same fp32 sum to fp16, so only accumulation-order flips of the last bit remain) -> 2e-4;
-attention observes ~2.5e-4 (P is rounded to fp16 before PV) -> 1.5e-3; norms observe <1e-4 -> 3e-4."""
+attention observes 2.5-2.9e-4 (P is rounded to fp16 before PV) -> 1.5e-3; norms observe 5-8e-6 -> 5e-5."""
 import pytest
 import torch
 
@@ -18,7 +18,7 @@ def _fp32_refs():
     torch.backends.cuda.matmul.allow_tf32 = False
 
 
-TOL_GEMM, TOL_ATTN, TOL_NORM = 2e-4, 1.5e-3, 3e-4
+TOL_GEMM, TOL_ATTN, TOL_NORM = 2e-4, 1.5e-3, 5e-5
 
 
 def gate(what, got, ref, tol):
@@ -56,6 +56,22 @@ def test_linear(M, N, K, hb, ha, bn):
     addend = rnd(g, M, N) if ha == 1 else (rnd(g, (M + ha - 1) // ha, N) if ha > 1 else None)
     out = nv.op_linear(a, w, bias, addend, ha if ha > 1 else 1, force_bn=bn)
     gate(f'linear {M}x{N}x{K}', out, ref_linear(a, w, bias, addend, ha), TOL_GEMM)
+
+
+@pytest.mark.parametrize("M,N,K,geglu_like", [(4096, 1280, 1280, False), (4096, 1280, 5120, False),
+                                              (4096, 3840, 1280, False), (2048, 640, 2560, False),
+                                              (8192, 1280, 1280, False), (5000, 1280, 640, False)])
+def test_linear_streamk_shapes_and_repeatability(M, N, K, geglu_like):
+    """Shapes whose tile count is not a multiple of the cluster count take the stream-K remainder path (partials parked
+    in the workspace by other clusters, self-resetting flags): result vs the fp32 reference, and 12 back-to-back
+    launches must be bit-identical (fixed summation order; flags re-armed by the kernel itself)."""
+    from cfgpp_b200 import _native as nv
+    g = torch.Generator().manual_seed(M + N + K)
+    a, w, bias, res = rnd(g, M, K), rnd(g, N, K, scale=K ** -0.5), rnd(g, N), rnd(g, M, N)
+    first = nv.op_linear(a, w, bias, res, 1)
+    gate(f'linear(stream-K) {M}x{N}x{K}', first, ref_linear(a, w, bias, res, 1), TOL_GEMM)
+    for _ in range(12):
+        assert torch.equal(nv.op_linear(a, w, bias, res, 1), first)
 
 
 def test_linear_dual_source_and_geglu():

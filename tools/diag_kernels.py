@@ -276,6 +276,64 @@ def diag_attn():
         guarded(name, run)
 
 
+def graph_time_us(fn, iters=40):
+    """Per-call device time of `fn` (enqueues on the current stream) replayed inside one CUDA graph."""
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(iters):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+    return 1e3 * e0.elapsed_time(e1) / iters
+
+
+def bench_gemm_graph():
+    """Graph-timed GEMM / GEGLU / conv launches at the SDXL shapes (UNet batch 4)."""
+    g = torch.Generator(device="cpu").manual_seed(2)
+    for (M, N, K, geglu) in [(4096, 1280, 1280, False), (4096, 3840, 1280, False), (4096, 1280, 5120, False),
+                             (4096, 10240, 1280, True), (16384, 640, 640, False), (16384, 1920, 640, False),
+                             (16384, 640, 2560, False), (16384, 5120, 640, True), (4096, 1280, 2560, False),
+                             (65536, 320, 960, False)]:
+        a = torch.randn(M, K, generator=g).half().to(dev)
+        w = (torch.randn(N, K, generator=g) * K ** -0.5).half().to(dev)
+        res = None if geglu else torch.randn(M, N, generator=g).half().to(dev)
+        bias = torch.randn(N, generator=g).half().to(dev)
+        us = graph_time_us(lambda: nv.op_linear(a, w, bias, res, 1, geglu=geglu))
+        print(f"gemm M={M} N={N} K={K} geglu={int(geglu)}: {us:7.1f} us  {2.0 * M * N * K / us / 1e6:6.0f} TFLOP/s", flush=True)
+    for (B, H, W, Cin, Cout) in [(4, 128, 128, 320, 320), (4, 64, 64, 640, 640), (4, 32, 32, 1280, 1280),
+                                 (4, 32, 32, 2560, 1280), (4, 64, 64, 1280, 640), (4, 128, 128, 640, 320)]:
+        x = torch.randn(B, H, W, Cin, generator=g).half().to(dev)
+        w = (torch.randn(Cout, 9 * Cin, generator=g) * (9 * Cin) ** -0.5).half().to(dev)
+        bias = torch.randn(Cout, generator=g).half().to(dev)
+        us = graph_time_us(lambda: nv.op_conv3x3(x, w, bias), iters=20)
+        print(f"conv B={B} {H}x{W} {Cin}->{Cout}: {us:7.1f} us  {2.0 * B * H * W * Cout * Cin * 9 / us / 1e6:6.0f} TFLOP/s", flush=True)
+
+
+def bench_attn():
+    """Graph-timed attention launches at the SDXL / SD v1.5 shapes (batch 2 => UNet batch 4)."""
+    g = torch.Generator(device="cpu").manual_seed(3)
+    for (B, H, Nq, Nkv, hd) in [(4, 20, 1024, 1024, 64), (4, 10, 4096, 4096, 64), (4, 20, 1024, 77, 64),
+                                (4, 10, 4096, 77, 64), (8, 8, 4096, 77, 40), (8, 8, 1024, 77, 80), (8, 8, 256, 77, 160),
+                                (8, 8, 4096, 4096, 40), (8, 8, 1024, 1024, 80)]:
+        P = (hd + 63) // 64 * 64
+        C = H * P
+        q = (torch.randn(B, Nq, C, generator=g) * 1.2).half().to(dev)
+        k = (torch.randn(B, Nkv, C, generator=g) * 1.2).half().to(dev)
+        v = (torch.randn(B, Nkv, C, generator=g) * 1.2).half().to(dev)
+        us = graph_time_us(lambda: nv.op_attention(q, k, v, H, head_dim=hd))
+        fl = 4.0 * B * H * Nq * Nkv * hd
+        print(f"attention B={B} H={H} Nq={Nq} Nkv={Nkv} hd={hd}: {us:7.1f} us  {fl / us / 1e6:7.0f} TFLOP/s", flush=True)
+
+
 def diag_norm():
     g = torch.Generator(device="cpu").manual_seed(4)
 
@@ -487,6 +545,10 @@ if __name__ == "__main__":
         diag_attn()
     if "norm" in which:
         diag_norm()
+    if "bench_attn" in which:
+        bench_attn()
+    if "bench_gemm_graph" in which:
+        bench_gemm_graph()
     if "unet_tiny" in which:
         diag_unet(("tiny_sdxl", "tiny_sd15"))
     if "unet_sdxl" in which:
