@@ -165,8 +165,12 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
   }
   const int dp_tiles = num_tiles - sk_r;
   auto sk_u0 = [&](int c) { return static_cast<int>(sk_units * c / num_clusters); };
-  Item sk_item[2];
-  int n_sk = 0;
+  // A cluster's stream-K share is at most one non-finishing piece (`sk_first`, walked FIRST so that its partial is
+  // published while everybody still has main-loop work) and at most one finishing piece (`sk_late`, walked just
+  // before the last data-parallel tile — or last when there is only one — so that the flag wait is never exposed,
+  // the heavier fix-up epilogue overlaps a main loop, and the accumulator stage of the parked piece is long free).
+  Item sk_first{}, sk_late{};
+  int n_first = 0, n_late = 0;
   if (sk_r > 0) {
     const int u0 = sk_u0(cluster_id), u1 = sk_u0(cluster_id + 1);
     if (u1 > u0) {
@@ -190,16 +194,28 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
         }
         return it;
       };
-      if (u1 > e0) sk_item[n_sk++] = make(s0 + 1, e0, u1);  // head of the next tile: never finishing, goes first
-      sk_item[n_sk++] = make(s0, u0, e0);
+      if (u1 > e0) {  // head of the next tile: never finishing
+        sk_first = make(s0 + 1, e0, u1);
+        n_first = 1;
+      }
+      const Item a = make(s0, u0, e0);
+      if (a.kind == kItemPart) {
+        sk_first = a;  // (a piece strictly inside one tile: then there is no second piece)
+        n_first = 1;
+      } else {
+        sk_late = a;
+        n_late = 1;
+      }
     }
   }
   const int n_dp = (dp_tiles > cluster_id) ? (dp_tiles - cluster_id + num_clusters - 1) / num_clusters : 0;
-  const int n_items = n_sk + n_dp;
+  const int n_items = n_first + n_late + n_dp;
+  const int late_pos = n_first + (n_dp >= 2 ? n_dp - 1 : n_dp);
   auto item_at = [&](int i) {
-    if (i < n_sk) return sk_item[i];
+    if (i < n_first) return sk_first;
+    if (n_late && i == late_pos) return sk_late;
     Item it;
-    it.tile = cluster_id + (i - n_sk) * num_clusters;
+    it.tile = cluster_id + (i - n_first - ((n_late && i > late_pos) ? 1 : 0)) * num_clusters;
     it.kb0 = 0;
     it.kb1 = nkb;
     it.kind = kItemFull;
@@ -207,7 +223,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
     return it;
   };
   constexpr unsigned kSkArrivals = CL * kEpiWarps;  // warps that publish / consume one cluster's partial
-  // partial accumulator of (cluster c, CTA rank r): [BN / 32 column chunks][128 rows][32] fp32
+  // partial accumulator of (cluster c, CTA rank r): [BN / 32 column chunks][4 lane quarters][8][32 lanes] float4
   auto sk_ws = [&](int c) { return p.sk_ws + (static_cast<size_t>(c) * CL + cta_rank) * (static_cast<size_t>(BM) * BN); };
 
   if (warp_idx == kProducerWarp) {
@@ -380,21 +396,25 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
           uint32_t v[32];
           tmem_ld_x32(t_base + jt * 32, v);
           tmem_ld_wait();
-          float4* dst = reinterpret_cast<float4*>(ws + (static_cast<size_t>(jt) * BM + row) * 32);
+          // lane-contiguous: float4 e of lane l sits at [e][l], so one STG.128 of the warp writes 512 contiguous bytes
+          // (a row-contiguous layout - 128 B per lane - makes every store 32 separate L1 wavefronts: 6.5 us per tile)
+          float4* dst = reinterpret_cast<float4*>(ws) + (static_cast<size_t>(jt) * 4 + q) * 256 + lane;
 #pragma unroll
           for (int e = 0; e < 8; ++e)
-            dst[e] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
-                                 __uint_as_float(v[4 * e + 3]));
+            dst[e * 32] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]),
+                                      __uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3]));
         }
         tc_fence_before();
-        __threadfence();  // this lane's partial is visible device-wide before the warp's arrival is counted
-        __syncwarp();
+        __syncwarp();  // the warp's stores happen-before lane 0's release below (barrier + cumulativity)
         if (lane == 0) {
           if constexpr (CL == 2)
             mbar_arrive_leader(&tmem_empty_bar[as]);
           else
             mbar_arrive(&tmem_empty_bar[as]);
-          atomicAdd(p.sk_flags + cluster_id, 1u);
+          // ONE release-add per warp publishes its part of the partial. (__threadfence() here — a fence.sc.gpu by all
+          // 256 epilogue threads — cost ~15 us per launch.)
+          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.sk_flags + cluster_id) : "memory");
+          if (leader) TL(15);
         }
         __syncwarp();
         continue;
@@ -405,10 +425,10 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
       auto add_partials = [&](uint32_t (&v)[32], int jt) {
         for (int c = item.c_first; c < cluster_id; ++c) {
           if (!contributes(c)) continue;
-          const float4* src = reinterpret_cast<const float4*>(sk_ws(c) + (static_cast<size_t>(jt) * BM + row) * 32);
+          const float4* src = reinterpret_cast<const float4*>(sk_ws(c)) + (static_cast<size_t>(jt) * 4 + q) * 256 + lane;
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const float4 f = __ldcg(src + e);
+            const float4 f = __ldcg(src + e * 32);
             v[4 * e] = __float_as_uint(__uint_as_float(v[4 * e]) + f.x);
             v[4 * e + 1] = __float_as_uint(__uint_as_float(v[4 * e + 1]) + f.y);
             v[4 * e + 2] = __float_as_uint(__uint_as_float(v[4 * e + 2]) + f.z);
@@ -469,17 +489,21 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
       if (leader) { if (it == 0) TL(7); TL(9); if (tl) tl[12] = it + 1; }
       tc_fence_after();
       if (full_res) mbar_wait(my_res_bar, (res_uses++) & 1);
-      if (fin) {  // every lane polls (acquire) until all warps of every contributing cluster have published
-        for (int c = item.c_first; c < cluster_id; ++c) {
-          if (!contributes(c)) continue;
-          unsigned seen;
-          do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.sk_flags + c) : "memory");
-            if (seen < kSkArrivals) __nanosleep(40);
-          } while (seen < kSkArrivals);
+      if (fin) {  // lane 0 polls (acquire) until all warps of every contributing cluster have published
+        if (leader) TL(13);
+        if (lane == 0) {
+          for (int c = item.c_first; c < cluster_id; ++c) {
+            if (!contributes(c)) continue;
+            unsigned seen;
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.sk_flags + c) : "memory");
+              if (seen < kSkArrivals) __nanosleep(32);
+            } while (seen < kSkArrivals);
+          }
         }
+        __syncwarp();  // the other lanes' partial loads (L2, __ldcg) are ordered after lane 0's acquire
+        if (leader) TL(14);
       }
-      if (leader && it == 0) TL(13);
       const uint32_t t_base = tmem_base + as * C::ACC_STRIDE + lane_off;
 
       // The arithmetic variant (LayerNorm fold / kind of addend / row statistics) is chosen ONCE per tile and the chunk
@@ -634,7 +658,6 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
         else
           chunks(std::false_type{});
       }
-      if (leader && it == 0) TL(14);
       tc_fence_before();
       fence_proxy_async_smem();  // this thread's part of the staging tile -> visible to the TMA engine
       __syncwarp();
@@ -733,7 +756,7 @@ double streamk_min_saved() {  // k-blocks of main loop the split must save per c
   static double v = -1.0;
   if (v < 0) {
     const char* e = getenv("CFGPP_STREAMK_MIN");
-    v = e ? atof(e) : 3.0;
+    v = e ? atof(e) : 40.0;
   }
   return v;
 }
@@ -808,8 +831,11 @@ void finish_op(GemmOp& op, const __half* w, int force_bn) {
   p.sk_flags = nullptr;
   const int rem = groups % max_clusters;
   if (streamk_enabled() && rem != 0 && max_clusters <= kSkMaxClusters) {
+    // main-loop work the split saves per cluster, in k-blocks of a 160-wide tile (~0.25 us each under the power cap):
+    // the parked partial and the fix-up cost ~2 us of epilogue, so short-K launches (K = 1280 projections: 5 k-blocks
+    // saved) keep the plain tile walk (measured: tools/diag_kernels.py bench_gemm_graph, CFGPP_STREAMK_MIN)
     const double piece = static_cast<double>(rem) * p.num_k_blocks / max_clusters;
-    const double saved = p.num_k_blocks - piece;
+    const double saved = (p.num_k_blocks - piece) * op.bn / 160.0;
     if (saved >= streamk_min_saved() && piece >= 2.0) {
       op.grid = op.cluster * max_clusters;  // all clusters take part, also when there are fewer tiles than clusters
       streamk_buffers(&p.sk_ws, &p.sk_flags);
@@ -858,8 +884,8 @@ GemmOp make_conv3x3_op(const __half* x, int B, int H, int W, int Cin, const __ha
   GemmParams& p = op.p;
   CFGPP_REQUIRE(Cin % BK == 0, "conv3x3 Cin must be a multiple of 64");
   CFGPP_REQUIRE(Cout % 8 == 0, "conv3x3 Cout must be a multiple of 8");
-  CFGPP_REQUIRE(conv3x3_geometry_supported(H, W), "conv3x3 needs power-of-two H, W with W <= 128");
-  const int Wt = W;
+  CFGPP_REQUIRE(conv3x3_geometry_supported(H, W), "conv3x3 needs power-of-two H, W (W <= 128) or W % 128 == 0");
+  const int Wt = W < BM ? W : BM;
   const int Ht = (BM / Wt) < H ? (BM / Wt) : H;
   const int Nt = BM / (Wt * Ht);
   p.M = B * H * W; p.N = Cout; p.K = 9 * Cin;

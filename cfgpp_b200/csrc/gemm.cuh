@@ -47,7 +47,7 @@ struct GemmParams {
   const float* ln_s;       // [N] fp32
   const float* ln_t;       // [N] fp32
   // ---- stream-K for the remainder tiles (see gemm.cu "work schedule"); null = plain data-parallel tile walk ------
-  float* sk_ws;            // per (cluster, CTA rank) partial accumulator [BN / 32][128][32] fp32
+  float* sk_ws;            // per (cluster, CTA rank) partial accumulator, 128 x BN fp32 in the epilogue's lane order
   unsigned* sk_flags;      // [2 * 256] zero-initialised, self-resetting arrival / consumer counters
 };
 
@@ -73,9 +73,12 @@ GemmOp make_conv3x3_op(const __half* x, int B, int H, int W, int Cin, const __ha
 
 void run_gemm_op(const GemmOp& op, cudaStream_t stream);
 
-// Geometry the implicit-GEMM A tile (a 4-D TMA box of whole image rows) can address: power-of-two H, W with W <= 128.
+// Geometry the implicit-GEMM A tile (a 4-D TMA box of 128 consecutive output pixels) can address: W <= 128 needs
+// power-of-two H, W (a tile = whole rows, possibly of several images); W > 128 needs W % 128 == 0 (a tile = a row segment).
 inline bool conv3x3_geometry_supported(int H, int W) {
-  return H >= 1 && W >= 1 && (W & (W - 1)) == 0 && (H & (H - 1)) == 0 && W <= 128;
+  if (H < 1 || W < 1) return false;
+  if (W > 128) return W % 128 == 0;
+  return (W & (W - 1)) == 0 && (H & (H - 1)) == 0;
 }
 
 }  // namespace cfgpp

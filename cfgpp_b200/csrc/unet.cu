@@ -108,6 +108,16 @@ int grid_for(size_t n) { return static_cast<int>(std::min<size_t>((n + 255) / 25
 void gemm_configure();
 void attn_configure();
 
+// shared with vae.cu (weight ingestion helpers)
+void run_f32_to_f16(const float* in, __half* out, size_t n, cudaStream_t stream) {
+  f32_to_f16_kernel<<<grid_for(n), 256, 0, stream>>>(in, out, n);
+  CFGPP_CHECK_CUDA(cudaGetLastError());
+}
+void run_pack_conv3x3(const __half* in, __half* out, int Cout, int Cin, cudaStream_t stream) {
+  pack_conv3x3_kernel<<<grid_for(static_cast<size_t>(Cout) * Cin * 9), 256, 0, stream>>>(in, out, Cout, Cin);
+  CFGPP_CHECK_CUDA(cudaGetLastError());
+}
+
 Unet::Unet(const cfgpp_model_desc& d, int device) : d_(d), device_(device) {
   CFGPP_CHECK_CUDA(cudaSetDevice(device));
   CFGPP_REQUIRE(d.num_levels >= 2 && d.num_levels <= CFGPP_MAX_LEVELS, "num_levels must be 2..4");

@@ -136,6 +136,32 @@ int cfgpp_get_state(cfgpp_handle* h, int which, void* out_dev, void* stream);
  * z0t / zt materialised between UNet calls). Applies schedule entry `step` to the internal state. */
 int cfgpp_apply_step(cfgpp_handle* h, int step, const void* eps_uc_dev, const void* eps_c_dev, void* stream);
 
+/* ---- AutoencoderKL decoder: replaces `self.vae.decode(zt / scaling_factor).sample` of
+ * latent_sdxl.py:155-164 (VAE madebyollin/sdxl-vae-fp16-fix, :44) and latent_diffusion.py:123-129 on the same conv /
+ * GEMM / GroupNorm kernels. Weights under the diffusers AutoencoderKL keys (`post_quant_conv.*`, `decoder.*`). ----- */
+typedef struct cfgpp_vae_desc {
+  int latent_channels;                       /* 4 */
+  int out_channels;                          /* 3 */
+  int num_levels;                            /* len(block_out_channels): 4 */
+  int block_out_channels[CFGPP_MAX_LEVELS];  /* (128, 256, 512, 512) */
+  int layers_per_block;                      /* 2 (the decoder's up blocks hold layers_per_block + 1 resnets) */
+  int norm_num_groups;                       /* 32 */
+  float scaling_factor;                      /* 0.13025 (SDXL) / 0.18215 (SD v1.5) */
+} cfgpp_vae_desc;
+typedef struct cfgpp_vae_handle cfgpp_vae_handle;
+int cfgpp_vae_create(const cfgpp_vae_desc* desc, int device, cfgpp_vae_handle** out);
+int cfgpp_vae_destroy(cfgpp_vae_handle* h);
+int cfgpp_vae_load_weight(cfgpp_vae_handle* h, const char* diffusers_key, const void* data_dev, const int64_t* shape,
+                          int ndim, int dtype, void* stream);
+int cfgpp_vae_finalize_weights(cfgpp_vae_handle* h, void* stream);
+/* zt_dev: (batch,4,h,w) NCHW of z_dtype — the SCALED latent the samplers return (the division by scaling_factor
+ * happens inside, in zt's dtype, as in the reference); image_dev: (batch,3,8h,8w) NCHW fp16 (num_levels = 4).
+ * The plan / workspace for (batch,h,w) is built on first use and cached. */
+int cfgpp_vae_decode(cfgpp_vae_handle* h, const void* zt_dev, int z_dtype, int batch, int h_lat, int w_lat,
+                     void* image_dev, void* stream);
+/* Algorithmic FLOPs of one decode of the prepared shape, and its activation workspace. */
+int cfgpp_vae_stats(cfgpp_vae_handle* h, double* flops, size_t* workspace_bytes);
+
 /* ---- operator-level entry points (one kernel each; used by the kernel parity tests and micro-benchmarks) ----- */
 int cfgpp_op_linear(const void* a, int lda, const void* a2, int lda2, int k_split, const void* w, int M, int N, int K,
                     const void* bias, const void* addend, int ld_add, int add_rows_per_group, void* out, int ldc,
