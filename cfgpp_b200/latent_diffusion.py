@@ -20,7 +20,7 @@ import torch
 
 from . import kdiffusion as K
 from . import schedule as S
-from .conditioning import LatentPreviewDecoder, SyntheticTextEncoder
+from .conditioning import SyntheticTextEncoder
 from .config import UNetConfig, sd15_config
 from .latent_sdxl import _Scheduler, get_engine
 
@@ -56,7 +56,11 @@ class StableDiffusion(K.KDiffusionMixin):
         self.cfg: UNetConfig = kwargs.get("unet_config") or sd15_config()
         self.unet = get_engine(model_key, self.cfg, device, kwargs.get("state_dict"))
         self.text_encoder = kwargs.get("text_encoder") or SyntheticTextEncoder(self.cfg.cross_attention_dim, 0)
-        self.vae = kwargs.get("vae") or LatentPreviewDecoder(self.cfg.vae_scale_factor)
+        self.vae = kwargs.get("vae")
+        if self.vae is None:
+            # AutoencoderKL decoder on the native backend (vae.py; the reference uses pipe.vae, latent_diffusion.py:64)
+            from .vae import get_vae
+            self.vae = get_vae("sd15_vae", device)
 
         self._sch = S.Schedule.make(solver_config.num_sampling, "ddim")
         self.total_alphas = self._sch.total_alphas

@@ -13,7 +13,7 @@ no host synchronisation; with a callback the un-fused seam (`predict_noise` + `a
 Registered here: ddim_cfg++, ddim_cfg++_lightning, dpm++_2m_cfgpp (the solvers of SURVEY.md §8a) and, from §8 f1,
 dpm++_2m_cfgpp_lightning (:932-952), ddim_edit_cfg++ (:954-1025, both loops on the fused step modes), euler_cfg++ and
 euler_cfg++_lightning (:757-836: native UNet behind `predict_noise`, the Euler update in torch — kdiffusion.py).
-Text encoders and the VAE stay on the reference path (see conditioning.py).
+The VAE decode runs on the native decoder (vae.py); text encoders stay pluggable (conditioning.py).
 """
 from __future__ import annotations
 
@@ -24,7 +24,7 @@ import torch
 
 from . import kdiffusion as K
 from . import schedule as S
-from .conditioning import LatentPreviewDecoder, SyntheticTextEncoder
+from .conditioning import SyntheticTextEncoder
 from .config import UNetConfig, sdxl_config
 from .engine import NativeUNet
 from .weights import load_safetensors_state_dict, synthetic_state_dict
@@ -125,7 +125,12 @@ class SDXL(K.KDiffusionMixin):
             SyntheticTextEncoder(d1 if d1 > 0 else self.cfg.cross_attention_dim // 2, 0),
             SyntheticTextEncoder(self.cfg.cross_attention_dim - (d1 if d1 > 0 else self.cfg.cross_attention_dim // 2),
                                  self.cfg.pooled_dim))
-        self.vae = vae or LatentPreviewDecoder(self.cfg.vae_scale_factor)
+        if vae is None:
+            # AutoencoderKL decoder on the native backend (vae.py; the reference loads madebyollin/sdxl-vae-fp16-fix,
+            # latent_sdxl.py:44). Pass `vae=` (any object with decode(zt) / encode(x, dtype)) to override.
+            from .vae import get_vae
+            vae = get_vae("sdxl_vae", device)
+        self.vae = vae
         self.vae_scale_factor = self.cfg.vae_scale_factor
         self.default_sample_size = self.cfg.sample_size
 

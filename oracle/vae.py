@@ -42,7 +42,7 @@ def sd15_vae_config() -> VAEConfig:
 
 
 def tiny_vae_config() -> VAEConfig:
-    return VAEConfig(name="tiny_vae", block_out_channels=(64, 128, 128), layers_per_block=1)
+    return VAEConfig(name="tiny_vae", block_out_channels=(64, 64, 128, 128), layers_per_block=1)
 
 
 class VaeResnetBlock2D(nn.Module):

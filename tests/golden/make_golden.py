@@ -94,8 +94,26 @@ def schedule_cases():
             "karras_6": OSm.karras_sigmas(OS.make_tables(6)).double()}
 
 
+def vae_case(seed=4242, hw=16):
+    """fp32-oracle decode of the tiny AutoencoderKL decoder on seeded CPU weights (tests/golden/r02_vae_golden.pt)."""
+    from cfgpp_b200 import vae as V
+    from oracle import vae as OV
+    cfg = V.tiny_vae_config()
+    sd = V.synthetic_vae_state_dict(cfg, seed=seed, device="cpu")
+    m = OV.build_vae_decoder(OV.VAEConfig(**{f.name: getattr(cfg, f.name) for f in dataclasses.fields(OV.VAEConfig)}), sd,
+                             dtype=torch.float32)
+    g = torch.Generator().manual_seed(77)
+    zt = torch.randn(1, 4, hw, hw, generator=g) * cfg.scaling_factor * 6.0
+    return {"seed": seed, "hw": hw, "zt": zt, "image": OV.decode(m, zt).half()}
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)  # summation order of the CPU kernels is part of the pin
+    if len(sys.argv) > 1 and sys.argv[1] == "vae":
+        out = Path(__file__).with_name("r02_vae_golden.pt")
+        torch.save({"vae": vae_case(), "torch": torch.__version__}, out)
+        print(out, out.stat().st_size, "bytes")
+        sys.exit(0)
     blob = {"schedule": schedule_cases(), "unet": {n: unet_case(n) for n in ("tiny_sdxl", "tiny_sd15")},
             "samplers": sampler_cases(), "torch": torch.__version__}
     out = Path(__file__).with_name("r01_golden.pt")

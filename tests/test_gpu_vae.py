@@ -1,0 +1,122 @@
+"""AutoencoderKL decoder through the C ABI against the oracle restatement (oracle/vae.py) on the same
+seeded weights: `decode(zt)` == `vae.decode(zt / scaling_factor).sample.float()` (latent_sdxl.py:155-164,
+latent_diffusion.py:123-129).
+
+Stated tolerance (same rule as the UNet forward): rel-L2 <= 5e-3 against the restated decoder under
+torch.autocast('cuda', fp16) — the reference's op sequence — AND the error against the fp32 oracle must not exceed
+1.5x the fp16 oracle's own. The single-head mid-block attention materialises the fp16 score matrix (head dim 512 does
+not fit the flash kernel), one extra rounding the reference's fused SDPA does not have; it stays inside the gate."""
+import dataclasses
+
+import pytest
+import torch
+
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+dev = torch.device("cuda:0")
+
+
+def _ocfg(cfg):
+    from oracle import vae as OV
+    return OV.VAEConfig(**{f.name: getattr(cfg, f.name) for f in dataclasses.fields(OV.VAEConfig)})
+
+
+def _case(kind, B, h, w, zdtype=torch.float32, seed=5, check32=True):
+    from cfgpp_b200 import vae as V
+    from oracle import vae as OV
+    cfg = V.VAE_CONFIGS[kind]()
+    sd = V.synthetic_vae_state_dict(cfg, seed=seed, device=dev)
+    g = torch.Generator().manual_seed(seed + 1)
+    zt = (torch.randn(B, 4, h, w, generator=g) * cfg.scaling_factor * 6.0).to(zdtype).to(dev)  # latents of std ~ 0.8
+    dec = V.NativeVAEDecoder(cfg, sd, dev)
+    got = dec.decode(zt)
+    assert got.dtype == torch.float32 and got.shape == (B, 3, 8 * h, 8 * w) and torch.isfinite(got).all()
+    again = dec.decode(zt)
+    assert torch.equal(got, again)  # deterministic, plan reuse
+    dec.close()
+    m16 = OV.build_vae_decoder(_ocfg(cfg), sd, dtype=torch.float16, device=dev)
+    with torch.autocast("cuda", dtype=torch.float16):
+        r16 = OV.decode(m16, zt)
+    del m16
+    e16 = rel_l2(got, r16)
+    msg = f"vae {kind} B={B} {h}x{w} z={zdtype}: vs fp16 oracle {e16:.3e}"
+    if check32:
+        m32 = OV.build_vae_decoder(_ocfg(cfg), sd, dtype=torch.float32, device=dev)
+        r32 = OV.decode(m32, zt.float())
+        del m32
+        e32, b32 = rel_l2(got, r32), rel_l2(r16, r32)
+        msg += f", vs fp32 oracle {e32:.3e} (fp16 oracle itself {b32:.3e})"
+        print(msg)
+        assert e32 <= 1.5 * b32 + 1e-4
+    else:
+        print(msg)
+    assert e16 <= 5e-3, msg
+    for i in range(B):
+        assert rel_l2(got[i], r16[i]) <= 5e-3
+
+
+@pytest.mark.parametrize("B,h,w,zdtype", [(1, 16, 16, torch.float32), (2, 32, 32, torch.float16), (3, 16, 32, torch.float32)])
+def test_vae_decode_tiny(B, h, w, zdtype):
+    _case("tiny_vae", B, h, w, zdtype)
+
+
+def test_vae_decode_sdxl_full_size():
+    """The real decoder geometry: 49.5 M parameters, 128x128 latent -> 1024x1024 image, attention over 16384 tokens."""
+    _case("sdxl_vae", 1, 128, 128)
+
+
+def test_vae_decode_sd15_512():
+    """SD v1.5: same architecture, scaling 0.18215, 64x64 latent -> 512x512, batch 2, fp16 latent (inversion path)."""
+    _case("sd15_vae", 2, 64, 64, torch.float16, check32=False)
+
+
+def test_vae_rejects_what_it_cannot_tile():
+    from cfgpp_b200 import _native as nv, vae as V
+    cfg = V.tiny_vae_config()
+    dec = V.NativeVAEDecoder(cfg, V.synthetic_vae_state_dict(cfg, device=dev), dev)
+    with pytest.raises(nv.NativeError):
+        dec.decode(torch.zeros(1, 4, 24, 24, device=dev))   # 24 -> 48, 96: not power-of-two below 128
+    ok = dec.decode(torch.zeros(1, 4, 16, 16, device=dev))   # still usable afterwards
+    assert ok.shape == (1, 3, 128, 128)
+    sd = V.synthetic_vae_state_dict(cfg, device=dev)
+    sd.pop("decoder.mid_block.attentions.0.to_v.bias")
+    with pytest.raises(KeyError):
+        V.NativeVAEDecoder(cfg, sd, dev)
+    dec.close()
+
+
+def test_solver_sample_decodes_with_native_vae():
+    """`sample()` end to end: latent from the fused trajectory -> native VAE -> image in [0, 1] on the CPU, equal to
+    decoding the solver's latent by hand (latent_sdxl.py:259-266)."""
+    from types import SimpleNamespace
+    from cfgpp_b200 import latent_sdxl as LX, vae as V
+    from cfgpp_b200.config import tiny_sdxl_config
+    from cfgpp_b200.utils.log_util import set_seed
+    s = LX.get_solver("ddim_cfg++", solver_config=SimpleNamespace(num_sampling=4), device="cuda:0",
+                      unet_config=tiny_sdxl_config(), model_key="synthetic:7")
+    assert isinstance(s.vae, V.NativeVAE)
+    set_seed(42)
+    img = s.sample(prompt1=["", "a cat"], prompt2=["", "a cat"], cfg_guidance=0.6, target_size=(256, 256))
+    assert img.shape == (1, 3, 256, 256) and img.device.type == "cpu" and 0 <= img.min() and img.max() <= 1
+    set_seed(42)
+    uc, c, pn, pc = s.get_text_embed("", "a cat", "", "a cat")
+    add = {"text_embeds": torch.cat([pn, pc]).to(dev), "time_ids": torch.tensor([[256., 256, 0, 0, 256, 256]] * 2).half().to(dev)}
+    z0 = s.reverse_process(uc, c, 0.6, add, (256, 256))
+    by_hand = (s.decode(z0) / 2 + 0.5).clamp(0, 1).cpu()
+    assert torch.equal(img, by_hand)
+    LX.release_engines()
+
+
+def test_native_vae_against_committed_golden():
+    """Native decode vs the COMMITTED fp32-oracle image (tests/golden/r02_vae_golden.pt, seeded CPU weights)."""
+    from pathlib import Path
+    from cfgpp_b200 import vae as V
+    gold = torch.load(Path(__file__).parent / "golden" / "r02_vae_golden.pt", weights_only=False)["vae"]
+    cfg = V.tiny_vae_config()
+    sd = {k: v.to(dev) for k, v in V.synthetic_vae_state_dict(cfg, seed=gold["seed"], device="cpu").items()}
+    dec = V.NativeVAEDecoder(cfg, sd, dev)
+    e = rel_l2(dec.decode(gold["zt"].to(dev)).cpu(), gold["image"].float())
+    print(f"tiny_vae vs golden fp32 image: rel-L2 {e:.3e}")
+    assert e <= 5e-3
+    dec.close()
