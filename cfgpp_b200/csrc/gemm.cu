@@ -83,7 +83,8 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
   uint64_t* tmem_full_bar = bars + 2 * C::STAGES;
   uint64_t* tmem_empty_bar = bars + 2 * C::STAGES + 2;
   uint64_t* res_bar = bars + 2 * C::STAGES + 4;  // [kEpiWarps]: each epilogue warp loads its own residual sub-blocks
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4 + kEpiWarps);
+  uint64_t* sk_pre_bar = bars + 2 * C::STAGES + 4 + kEpiWarps;  // stream-K: the finishing piece's accumulator is preloaded
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4 + kEpiWarps + 1);
 
   const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
@@ -112,6 +113,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
       mbar_init(&tmem_empty_bar[i], CL * kEpiWarps);  // one elected arrive per epilogue warp (pair: of both CTAs)
     }
     for (int i = 0; i < kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+    mbar_init(sk_pre_bar, CL * kEpiWarps);
     fence_barrier_init();
   }
   if constexpr (CL > 1) cluster_sync_all();  // both CTAs resident before the pair-wide TMEM allocation
@@ -147,12 +149,11 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
   // the R = T mod clusters left-over tiles would cost a full extra round with most clusters idle, so their
   // R * nkb k-blocks are split evenly over ALL clusters instead: cluster c owns the contiguous unit range
   // [c U / P, (c + 1) U / P) of the linearised (tile, k-block) space — at most two pieces, of two adjacent tiles. The
-  // piece that contains a tile's LAST k-block finishes the tile: it adds the fp32 partial accumulators the other
-  // pieces parked in the workspace (fixed order: deterministic) and runs the normal epilogue. Stream-K items come
-  // first, the non-finishing piece ahead of the finishing one, so that partials are published early and the fix-up
-  // epilogue overlaps the following data-parallel main loops. All clusters of the grid are co-resident (grid <= SMs,
+  // piece that contains a tile's LAST k-block finishes the tile: the fp32 partial accumulators the other pieces
+  // parked in the workspace are summed in a fixed order (deterministic) and preloaded into its TMEM accumulator, its
+  // MMAs accumulate on top and the normal epilogue follows. All clusters of the grid are co-resident (grid <= SMs,
   // one CTA per SM; a dependent grid is only scheduled after every CTA of this one has started), so the spin-wait
-  // on a peer's flag cannot deadlock.
+  // on a peer's flag cannot deadlock; a waits-for edge always points at a lower cluster's FIRST item.
   constexpr int kItemFull = 0, kItemPart = 1, kItemFin = 2;
   struct Item {
     int tile, kb0, kb1, kind, c_first;
@@ -304,6 +305,8 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&tmem_empty_bar[as], aph ^ 1);
+        const bool preloaded = (item.kind == kItemFin);  // the epilogue warps stored the other pieces' partial sum
+        if (preloaded) mbar_wait(sk_pre_bar, 0);         // into this accumulator stage: accumulate on top of it
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * C::ACC_STRIDE;
         for (int kb = kb_first; kb <= kb_last; ++kb) {
@@ -321,9 +324,9 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
             for (int k = 0; k < BK / 16; ++k) {
               // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
               if constexpr (CL == 1)
-                umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb != kb_first || k != 0) ? 1u : 0u);
+                umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (preloaded || kb != kb_first || k != 0) ? 1u : 0u);
               else
-                umma_f16_cg2(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb != kb_first || k != 0) ? 1u : 0u);
+                umma_f16_cg2(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (preloaded || kb != kb_first || k != 0) ? 1u : 0u);
             }
             // on retirement: free the smem slot (pair: in both CTAs) and, after the last k-block, publish the
             // accumulator
@@ -380,7 +383,78 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
       if (i0 < n_items) issue_residual(item_at(i0).tile);
     }
     int res_uses = 0;
+    // Stream-K fix-up: the partial accumulators the other clusters parked for this cluster's finishing piece are summed
+    // (fixed order) and STORED INTO THE TMEM STAGE that piece will use, so its MMAs simply accumulate on top and its
+    // epilogue is the ordinary one. This runs one item early — under the main loop of the data-parallel tile before
+    // the finishing piece — so the L2 round trips of the partial loads (~1 us per chunk and contributor) are hidden.
+    const bool has_fin = n_late && sk_late.kind == kItemFin;
+    const int pre_iter = (late_pos - 1 >= n_first) ? late_pos - 1 : late_pos;
+    auto sk_preload = [&]() {
+      auto contributes = [&](int c) { return sk_u0(c + 1) > sk_u0(c); };
+      if (leader) TL(13);
+      if (lane == 0) {  // acquire: every warp of every contributing cluster has published its partial
+        for (int c = sk_late.c_first; c < cluster_id; ++c) {
+          if (!contributes(c)) continue;
+          unsigned seen;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.sk_flags + c) : "memory");
+            if (seen < kSkArrivals) __nanosleep(32);
+          } while (seen < kSkArrivals);
+        }
+      }
+      __syncwarp();  // the other lanes' partial loads (L2, __ldcg) are ordered after lane 0's acquire
+      if (leader) TL(14);
+      const uint32_t t_base = tmem_base + (late_pos & 1) * C::ACC_STRIDE + lane_off;
+#pragma unroll 1
+      for (int jt = half; jt < BN / 32; jt += 2) {
+        uint32_t v[32];
+        bool first = true;
+        for (int c = sk_late.c_first; c < cluster_id; ++c) {
+          if (!contributes(c)) continue;
+          const float4* src = reinterpret_cast<const float4*>(sk_ws(c)) + (static_cast<size_t>(jt) * 4 + q) * 256 + lane;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float4 f = __ldcg(src + e * 32);
+            if (first) {
+              v[4 * e] = __float_as_uint(f.x);
+              v[4 * e + 1] = __float_as_uint(f.y);
+              v[4 * e + 2] = __float_as_uint(f.z);
+              v[4 * e + 3] = __float_as_uint(f.w);
+            } else {
+              v[4 * e] = __float_as_uint(__uint_as_float(v[4 * e]) + f.x);
+              v[4 * e + 1] = __float_as_uint(__uint_as_float(v[4 * e + 1]) + f.y);
+              v[4 * e + 2] = __float_as_uint(__uint_as_float(v[4 * e + 2]) + f.z);
+              v[4 * e + 3] = __float_as_uint(__uint_as_float(v[4 * e + 3]) + f.w);
+            }
+          }
+          first = false;
+        }
+        tmem_st_x32(t_base + jt * 32, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CL == 2)
+          mbar_arrive_leader(sk_pre_bar);
+        else
+          mbar_arrive(sk_pre_bar);
+        // this warp has consumed the partials: the last of the kSkArrivals consumers re-arms the contributor's flag,
+        // so the buffers are back in their initial state when the kernel ends (CUDA-graph replays bake the arguments,
+        // an epoch counter is not an option)
+        for (int c = sk_late.c_first; c < cluster_id; ++c) {
+          if (!contributes(c)) continue;
+          const unsigned old = atomicAdd(p.sk_flags + kSkDoneOffset + c, 1u);
+          if (old == kSkArrivals - 1) {
+            p.sk_flags[kSkDoneOffset + c] = 0u;
+            p.sk_flags[c] = 0u;
+          }
+        }
+      }
+      __syncwarp();
+    };
     for (int it = 0; it < n_items; ++it) {
+      if (has_fin && it == pre_iter) sk_preload();
       const Item item = item_at(it);
       const int tile = item.tile;
       const int as = it & 1;
@@ -419,23 +493,6 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
         __syncwarp();
         continue;
       }
-      const bool fin = (item.kind == kItemFin);
-      auto contributes = [&](int c) { return sk_u0(c + 1) > sk_u0(c); };
-      // v[0..32) += the partials parked by the clusters that hold the earlier k-blocks of this tile (fixed order)
-      auto add_partials = [&](uint32_t (&v)[32], int jt) {
-        for (int c = item.c_first; c < cluster_id; ++c) {
-          if (!contributes(c)) continue;
-          const float4* src = reinterpret_cast<const float4*>(sk_ws(c)) + (static_cast<size_t>(jt) * 4 + q) * 256 + lane;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float4 f = __ldcg(src + e * 32);
-            v[4 * e] = __float_as_uint(__uint_as_float(v[4 * e]) + f.x);
-            v[4 * e + 1] = __float_as_uint(__uint_as_float(v[4 * e + 1]) + f.y);
-            v[4 * e + 2] = __float_as_uint(__uint_as_float(v[4 * e + 2]) + f.z);
-            v[4 * e + 3] = __float_as_uint(__uint_as_float(v[4 * e + 3]) + f.w);
-          }
-        }
-      };
       const int m_blk = tile_m_blk(tile);
       const int n_blk = tile_n_blk(tile);
       const int m = m_blk * BM + row;
@@ -489,21 +546,6 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
       if (leader) { if (it == 0) TL(7); TL(9); if (tl) tl[12] = it + 1; }
       tc_fence_after();
       if (full_res) mbar_wait(my_res_bar, (res_uses++) & 1);
-      if (fin) {  // lane 0 polls (acquire) until all warps of every contributing cluster have published
-        if (leader) TL(13);
-        if (lane == 0) {
-          for (int c = item.c_first; c < cluster_id; ++c) {
-            if (!contributes(c)) continue;
-            unsigned seen;
-            do {
-              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.sk_flags + c) : "memory");
-              if (seen < kSkArrivals) __nanosleep(32);
-            } while (seen < kSkArrivals);
-          }
-        }
-        __syncwarp();  // the other lanes' partial loads (L2, __ldcg) are ordered after lane 0's acquire
-        if (leader) TL(14);
-      }
       const uint32_t t_base = tmem_base + as * C::ACC_STRIDE + lane_off;
 
       // The arithmetic variant (LayerNorm fold / kind of addend / row statistics) is chosen ONCE per tile and the chunk
@@ -520,7 +562,6 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
             uint32_t v[32];
             tmem_ld_x32(t_base + j * 32, v);
             tmem_ld_wait();
-            if (fin) add_partials(v, j);
             const int n0 = n_blk * BN + j * 32;
             uint8_t* srow = my_row + j * C::EPI_SUB_BYTES;
 #pragma unroll
@@ -601,10 +642,6 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
             tmem_ld_x32(t_base + j * 32, va);
             tmem_ld_x32(t_base + BN / 2 + j * 32, vg);
             tmem_ld_wait();
-            if (fin) {
-              add_partials(va, j);
-              add_partials(vg, BN / 64 + j);
-            }
             uint8_t* srow = my_row + j * C::EPI_SUB_BYTES;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -677,19 +714,6 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
           const int nx = next_res_item(it + 1);
           if (nx < n_items) issue_residual(item_at(nx).tile);
         }
-        if (fin) {
-          // this warp has consumed the partials: the last of the kSkArrivals consumers re-arms the contributor's
-          // flag, so the buffers are back in their initial state when the kernel ends (CUDA-graph replays bake the
-          // arguments, an epoch counter is not an option)
-          for (int c = item.c_first; c < cluster_id; ++c) {
-            if (!contributes(c)) continue;
-            const unsigned old = atomicAdd(p.sk_flags + kSkDoneOffset + c, 1u);
-            if (old == kSkArrivals - 1) {
-              p.sk_flags[kSkDoneOffset + c] = 0u;
-              p.sk_flags[c] = 0u;
-            }
-          }
-        }
       }
       __syncwarp();
       // (written after the tmem_empty arrive: a global store ahead of that cluster-scope release would delay it)
@@ -756,7 +780,15 @@ double streamk_min_saved() {  // k-blocks of main loop the split must save per c
   static double v = -1.0;
   if (v < 0) {
     const char* e = getenv("CFGPP_STREAMK_MIN");
-    v = e ? atof(e) : 40.0;
+    v = e ? atof(e) : 4.0;
+  }
+  return v;
+}
+double streamk_min_piece() {  // smallest piece as a fraction of a tile's k-blocks (CFGPP_STREAMK_PIECE overrides)
+  static double v = -1.0;
+  if (v < 0) {
+    const char* e = getenv("CFGPP_STREAMK_PIECE");
+    v = e ? atof(e) : 0.5;
   }
   return v;
 }
@@ -836,7 +868,8 @@ void finish_op(GemmOp& op, const __half* w, int force_bn) {
     // saved) keep the plain tile walk (measured: tools/diag_kernels.py bench_gemm_graph, CFGPP_STREAMK_MIN)
     const double piece = static_cast<double>(rem) * p.num_k_blocks / max_clusters;
     const double saved = (p.num_k_blocks - piece) * op.bn / 160.0;
-    if (saved >= streamk_min_saved() && piece >= 2.0) {
+    // pieces at least half a tile deep: a tile then has at most three pieces, i.e. <= 2 partials to sum per chunk
+    if (saved >= streamk_min_saved() && piece >= 2.0 && piece >= streamk_min_piece() * p.num_k_blocks) {
       op.grid = op.cluster * max_clusters;  // all clusters take part, also when there are fewer tiles than clusters
       streamk_buffers(&p.sk_ws, &p.sk_flags);
     }
