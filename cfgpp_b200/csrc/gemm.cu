@@ -784,6 +784,14 @@ double streamk_min_saved() {  // k-blocks of main loop the split must save per c
   }
   return v;
 }
+bool streamk_linear() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CFGPP_STREAMK_LINEAR");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 double streamk_min_piece() {  // smallest piece as a fraction of a tile's k-blocks (CFGPP_STREAMK_PIECE overrides)
   static double v = -1.0;
   if (v < 0) {
@@ -863,13 +871,18 @@ void finish_op(GemmOp& op, const __half* w, int force_bn) {
   p.sk_flags = nullptr;
   const int rem = groups % max_clusters;
   if (streamk_enabled() && rem != 0 && max_clusters <= kSkMaxClusters) {
-    // main-loop work the split saves per cluster, in k-blocks of a 160-wide tile (~0.25 us each under the power cap):
-    // the parked partial and the fix-up cost ~2 us of epilogue, so short-K launches (K = 1280 projections: 5 k-blocks
-    // saved) keep the plain tile walk (measured: tools/diag_kernels.py bench_gemm_graph, CFGPP_STREAMK_MIN)
+    // Policy from measurements (tools/diag_kernels.py bench_gemm_graph, graph-timed, same box, with / without):
+    //   conv3x3 1280->1280 @32x32 (180 k-blocks)  119.4 -> 108.7 us     2560->1280  234.7 -> 210.2 us
+    //   conv3x3 640->640 @64x64 (90 k-blocks)     122.1 -> 109.6 us
+    //   linear K = 5120 (80 k-blocks)              47.1 ->  50.2 us     K = 1280 (20)  17.3 -> 25.8 us   GEGLU 82 -> 93
+    // The parked partial + preload cost a fixed ~8 us per launch that only main loops of >= ~90 k-blocks amortise, so
+    // the implicit-GEMM convolutions take the split and the linear layers keep the plain tile walk
+    // (CFGPP_STREAMK_LINEAR=1 forces it on for them; CFGPP_STREAMK_MIN / _PIECE tune the thresholds).
     const double piece = static_cast<double>(rem) * p.num_k_blocks / max_clusters;
     const double saved = (p.num_k_blocks - piece) * op.bn / 160.0;
+    const bool eligible = p.conv || streamk_linear();
     // pieces at least half a tile deep: a tile then has at most three pieces, i.e. <= 2 partials to sum per chunk
-    if (saved >= streamk_min_saved() && piece >= 2.0 && piece >= streamk_min_piece() * p.num_k_blocks) {
+    if (eligible && saved >= streamk_min_saved() && piece >= 2.0 && piece >= streamk_min_piece() * p.num_k_blocks) {
       op.grid = op.cluster * max_clusters;  // all clusters take part, also when there are fewer tiles than clusters
       streamk_buffers(&p.sk_ws, &p.sk_flags);
     }

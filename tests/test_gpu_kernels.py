@@ -62,9 +62,11 @@ def test_linear(M, N, K, hb, ha, bn):
                                               (4096, 3840, 1280, False), (2048, 640, 2560, False),
                                               (8192, 1280, 1280, False), (5000, 1280, 640, False)])
 def test_linear_streamk_shapes_and_repeatability(M, N, K, geglu_like):
-    """Shapes whose tile count is not a multiple of the cluster count take the stream-K remainder path (partials parked
-    in the workspace by other clusters, self-resetting flags): result vs the fp32 reference, and 12 back-to-back
-    launches must be bit-identical (fixed summation order; flags re-armed by the kernel itself)."""
+    """Shapes whose tile count is not a multiple of the cluster count CAN take the stream-K remainder path (partials
+    parked in the workspace by other clusters, self-resetting flags; on by default for the convolutions, for linear
+    layers with CFGPP_STREAMK_LINEAR=1 CFGPP_STREAMK_MIN=0 CFGPP_STREAMK_PIECE=0 — the round-2 GPU runs exercise
+    both settings): result vs the fp32 reference, and 12 back-to-back launches must be bit-identical (fixed summation
+    order; flags re-armed by the kernel itself)."""
     from cfgpp_b200 import _native as nv
     g = torch.Generator().manual_seed(M + N + K)
     a, w, bias, res = rnd(g, M, K), rnd(g, N, K, scale=K ** -0.5), rnd(g, N), rnd(g, M, N)
@@ -92,6 +94,17 @@ def test_linear_dual_source_and_geglu():
     h = (a.float() @ w.float().t() + b.float()).half()
     ref = (h[:, :inner].float() * torch.nn.functional.gelu(h[:, inner:].float()).half().float()).half()
     gate('geglu', out, ref, TOL_GEMM)
+
+
+def test_conv3x3_streamk_repeatable():
+    """The conv shapes of the 1280-channel level take the stream-K split by default: 10 launches, bit-identical."""
+    from cfgpp_b200 import _native as nv
+    g = torch.Generator().manual_seed(11)
+    x, w, bias = rnd(g, 4, 32, 32, 1280), rnd(g, 1280, 9 * 1280, scale=(9 * 1280) ** -0.5), rnd(g, 1280)
+    res = rnd(g, 4 * 32 * 32, 1280)
+    first = nv.op_conv3x3(x, w, bias, res, 1)
+    for _ in range(10):
+        assert torch.equal(nv.op_conv3x3(x, w, bias, res, 1), first)
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,ht,hr", [
