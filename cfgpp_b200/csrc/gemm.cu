@@ -439,6 +439,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
           mbar_arrive_leader(sk_pre_bar);
         else
           mbar_arrive(sk_pre_bar);
+        if (leader) TL(7);
         // this warp has consumed the partials: the last of the kSkArrivals consumers re-arms the contributor's flag,
         // so the buffers are back in their initial state when the kernel ends (CUDA-graph replays bake the arguments,
         // an epoch counter is not an option)
@@ -543,7 +544,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
       float ps = 0.f, pss = 0.f;  // producer side: partial row statistics of this warp's columns of the tile
       named_bar_sync(1, kEpiWarps * 32);  // staged vectors visible to all epilogue threads
       mbar_wait(&tmem_full_bar[as], aph);
-      if (leader) { if (it == 0) TL(7); TL(9); if (tl) tl[12] = it + 1; }
+      if (leader) { TL(9); if (tl) tl[12] = it + 1; }
       tc_fence_after();
       if (full_res) mbar_wait(my_res_bar, (res_uses++) & 1);
       const uint32_t t_base = tmem_base + as * C::ACC_STRIDE + lane_off;

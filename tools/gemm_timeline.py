@@ -13,7 +13,7 @@ from cfgpp_b200 import _native as nv  # noqa: E402
 dev = torch.device("cuda:0")
 lib = nv.load()
 names = ["entry", "prologue_done", "pdl_wait_done", "first_tma", "first_full", "tile0_lastkb", "lasttile_lastkb",
-         "epi0_start", "epi0_store", "epiL_start", "epiL_store", "exit", "ntiles", "sk_fin_wait", "sk_fin_seen", "sk_part_published"]
+         "sk_preload_done", "epi0_store", "epiL_start", "epiL_store", "exit", "ntiles", "sk_fin_wait", "sk_fin_seen", "sk_part_published"]
 for (M, N, K, res, bn) in [(4096, 1280, 1280, False, 0), (4096, 1280, 1280, True, 0), (4096, 1280, 5120, True, 0),
                            (4096, 3840, 1280, False, 0), (16384, 640, 640, True, 0), (8192, 8192, 8192, False, 256)
                            ][: int(sys.argv[1]) if len(sys.argv) > 1 else None]:
