@@ -29,6 +29,10 @@ void attn_configure();
 void xattn_configure();
 bool xattn_applicable(const AttnOp& op);
 void run_xattn_op(const AttnOp& op, cudaStream_t stream);
+// attention_persist.cu: persistent self-attention for head dim 64 (one CTA per SM, balanced tile ranges)
+void attn_persist_configure();
+bool attn_persist_applicable(const AttnOp& op);
+void run_attn_persist_op(const AttnOp& op, cudaStream_t stream);
 
 namespace {
 
@@ -374,6 +378,7 @@ void attn_configure() {
   configure_one<128, 1, 2>();
   configure_one<192, 1, 1>();
   xattn_configure();
+  attn_persist_configure();
   done = true;
 }
 
@@ -386,6 +391,12 @@ void run_attn_op(const AttnOp& op, cudaStream_t stream) {
     return e != nullptr && e[0] == '1';
   }();
   if (!no_x && xattn_applicable(op)) return run_xattn_op(op, stream);
+  // head dim 64 with at least two query tiles per SM: persistent kernel (CFGPP_NO_PATTN=1 keeps the pair-per-CTA grid)
+  static const bool no_p = [] {
+    const char* e = std::getenv("CFGPP_NO_PATTN");
+    return e != nullptr && e[0] == '1';
+  }();
+  if (!no_p && attn_persist_applicable(op)) return run_attn_persist_op(op, stream);
   attn_configure();
   switch (op.hd_pad) {
     case 64: return launch<64, 2, 3>(op, stream);

@@ -138,7 +138,10 @@ def test_conv3x3(B, H, W, Cin, Cout, ht, hr):
                                         (4, 20, 1024, 77), (1, 2, 200, 333), (1, 1, 1, 1),
                                         # single-KV-tile (cross-attention) kernel: 80- and 128-column variants,
                                         # uneven tiles per CTA, a partial last query tile
-                                        (4, 10, 4096, 77), (1, 5, 1024, 128), (2, 3, 520, 100), (1, 2, 256, 5)])
+                                        (4, 10, 4096, 77), (1, 5, 1024, 128), (2, 3, 520, 100), (1, 2, 256, 5),
+                                        # persistent self-attention kernel (>= 2 query tiles per SM): the bench shape,
+                                        # ragged Nq / Nkv, ranges that straddle heads and batches, exactly 2 per SM
+                                        (4, 20, 1024, 1024), (3, 13, 1100, 1000), (1, 37, 1024, 640), (2, 31, 700, 333)])
 def test_attention(B, H, Nq, Nkv):
     from cfgpp_b200 import _native as nv
     g = torch.Generator().manual_seed(Nq + Nkv)
@@ -157,7 +160,8 @@ def test_attention(B, H, Nq, Nkv):
 
 @pytest.mark.parametrize("B,H,Nq,Nkv,hd", [(2, 8, 1024, 1024, 80), (1, 8, 4096, 4096, 40), (2, 8, 256, 256, 160),
                                            (2, 8, 64, 77, 160), (1, 3, 300, 77, 40), (2, 8, 1024, 77, 80),
-                                           (2, 8, 256, 77, 160), (1, 4, 4096, 77, 40), (1, 2, 640, 120, 160)])
+                                           (2, 8, 256, 77, 160), (1, 4, 4096, 77, 40), (1, 2, 640, 120, 160),
+                                           (2, 8, 4096, 4096, 40)])
 def test_attention_padded_heads(B, H, Nq, Nkv, hd):
     """SD v1.5 head dims (40 / 80 / 160): heads are zero-padded to a multiple of 64 columns in q / k / v."""
     from cfgpp_b200 import _native as nv
