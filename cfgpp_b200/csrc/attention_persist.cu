@@ -119,19 +119,37 @@ attn_persist_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_
       // ===================== TMA producer of one slot =====================
       const int s = warp_idx == 0 ? 0 : 1;
       const int items = n_items(s);
-      int g = 0;  // K / V tiles loaded so far (ring position carries across query tiles)
-      for (int it = 0; it < items; ++it) {
-        const TileCoord c = coord(s, it);
-        mbar_wait(bar(s, Q_EMPTY), (it & 1) ^ 1);  // every QK^T of the previous tile has retired
-        mbar_arrive_expect_tx(bar(s, Q_FULL), TILE_BYTES);
-        tma_load_3d(sQ(s), &map_q, bar(s, Q_FULL), c.head * HD, c.q0, c.batch);
-        for (int j = 0; j < n_tiles; ++j, ++g) {
-          const int st = g % KS;
-          const uint32_t ph = (g / KS) & 1;
-          mbar_wait(bar(s, K_EMPTY + st), ph ^ 1);
+      // K runs one tile ahead of V (K0, K1 V0, K2 V1, ...): a V stage is only recycled when PV(g-2) has retired,
+      // late in step g-1; waiting for it BEFORE issuing K(g+1) would hand the tensor pipe its next K tile late.
+      const int total_g = items * n_tiles;
+      auto tile_of = [&](int g, TileCoord& c, int& j) {
+        const int it = g / n_tiles;
+        j = g - it * n_tiles;
+        c = coord(s, it);
+        return it;
+      };
+      for (int i = 0; i <= total_g; ++i) {
+        if (i < total_g) {
+          TileCoord c;
+          int j;
+          const int it = tile_of(i, c, j);
+          if (j == 0) {
+            mbar_wait(bar(s, Q_EMPTY), (it & 1) ^ 1);  // every QK^T of the previous tile has retired
+            mbar_arrive_expect_tx(bar(s, Q_FULL), TILE_BYTES);
+            tma_load_3d(sQ(s), &map_q, bar(s, Q_FULL), c.head * HD, c.q0, c.batch);
+          }
+          const int st = i % KS;
+          mbar_wait(bar(s, K_EMPTY + st), ((i / KS) & 1) ^ 1);
           mbar_arrive_expect_tx(bar(s, K_FULL + st), TILE_BYTES);
           tma_load_3d(sK(s, st), &map_k, bar(s, K_FULL + st), c.head * HD, j * BKV, c.batch);
-          mbar_wait(bar(s, V_EMPTY + st), ph ^ 1);
+        }
+        if (i >= 1) {
+          const int g = i - 1;
+          TileCoord c;
+          int j;
+          tile_of(g, c, j);
+          const int st = g % KS;
+          mbar_wait(bar(s, V_EMPTY + st), ((g / KS) & 1) ^ 1);
           mbar_arrive_expect_tx(bar(s, V_FULL + st), TILE_BYTES);
           tma_load_3d(sV(s, st), &map_v, bar(s, V_FULL + st), c.head * HD, j * BKV, c.batch);
         }

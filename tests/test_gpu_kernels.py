@@ -206,3 +206,17 @@ def test_layernorm(M, Cc):
     x, gamma, beta = rnd(g, M, Cc, scale=3.0, shift=1.0), rnd(g, Cc, scale=0.2, shift=1.0), rnd(g, Cc, scale=0.2)
     ref = torch.nn.functional.layer_norm(x.float(), (Cc,), gamma.float(), beta.float(), 1e-5).half()
     gate(f'layernorm {M}x{Cc}', nv.op_layernorm(x, gamma, beta), ref, TOL_NORM)
+
+
+def test_attention_persistent_variant_in_subprocess():
+    """The opt-in persistent self-attention kernel (CFGPP_PATTN=1, attention_persist.cu) is kept validated: the
+    attention parity tests re-run in a child process with the switch set (the dispatch reads it once per process)."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("CFGPP_PATTN") == "1":
+        pytest.skip("already inside the child")
+    env = dict(os.environ, CFGPP_PATTN="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-k",
+                        "test_attention and not subprocess", "-x"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
