@@ -218,23 +218,30 @@ CFGPP_DEVICE void cfgpp_update(int mode, const StepCoef& k, float eu, float ec, 
     const float b = rh(__fmul_rn(k.c3, e_rn));
     z_new = rs<kHalfState>(__fadd_rn(rs<kHalfState>(__fmul_rn(k.c2, z0t)), b));
   } else {  // STEP_DPMPP2M_CFGPP (state is fp16 in the reference; kHalfState expected)
+    // Family of VE-cast ("k-diffusion") updates on the Tweedie estimates  den = x - sigma eps_guided,
+    // ud = x - sigma eps_uc.  k.second_order bits: 1 = second-order (2M) branch; 2 = EXTRAPOLATE with the guided
+    // estimate instead of the unconditional one (plain-CFG euler / dpm++_2m: latent_diffusion.py:326-330, :470-487);
+    // 4 = the 2M difference term uses the guided estimate (SD v1.5 `dpm++_2m_cfg++`, latent_diffusion.py:863, whereas
+    // SDXL's `dpm++_2m_cfgpp` uses the unconditional one, latent_sdxl.py:916).
     const float den = rs<kHalfState>(__fadd_rn(z, rh(__fmul_rn(k.c0, np))));
     const float ud = rs<kHalfState>(__fadd_rn(z, rh(__fmul_rn(k.c0, eu))));
+    const float ex = (k.second_order & 2) ? den : ud;
     z0t = den;
-    if (!k.second_order) {
-      float d = rs<kHalfState>(__fsub_rn(z, ud));
+    if (!(k.second_order & 1)) {
+      float d = rs<kHalfState>(__fsub_rn(z, ex));
       d = rs<kHalfState>(__fmul_rn(d, k.c1));  // / sigma_i  (scalar divisor -> reciprocal multiply on CUDA)
       d = rs<kHalfState>(__fmul_rn(d, k.c2));  // * sigma_{i+1}
       z_new = rs<kHalfState>(__fadd_rn(den, d));
     } else {
-      const float e1a = rs<kHalfState>(__fmul_rn(k.d0, ud));
-      float e1b = rs<kHalfState>(__fmul_rn(k.d1, rs<kHalfState>(__fsub_rn(ud, old_d))));
+      const float df = (k.second_order & 4) ? den : ud;
+      const float e1a = rs<kHalfState>(__fmul_rn(k.d0, ex));
+      float e1b = rs<kHalfState>(__fmul_rn(k.d1, rs<kHalfState>(__fsub_rn(df, old_d))));
       e1b = rs<kHalfState>(__fmul_rn(e1b, k.d2));  // / (2 r)
       const float extra1 = rs<kHalfState>(__fsub_rn(e1a, e1b));
       const float extra2 = rs<kHalfState>(__fmul_rn(k.d3, z));
       z_new = rs<kHalfState>(__fadd_rn(rs<kHalfState>(__fadd_rn(den, extra1)), extra2));
     }
-    new_old = ud;
+    new_old = ex;
   }
 }
 
@@ -252,7 +259,7 @@ CFGPP_DEVICE void apply_step_elem(int mode, int half_state, const StepCoef& k, f
                                   void* z0t_out, size_t i) {
   const bool hs = half_state != 0;
   const float zv = load_state(z, i, hs);
-  const float old_d = (mode == STEP_DPMPP2M_CFGPP && k.second_order) ? load_state(aux, i, hs) : 0.f;
+  const float old_d = (mode == STEP_DPMPP2M_CFGPP && (k.second_order & 1)) ? load_state(aux, i, hs) : 0.f;
   float zn, z0, no;
   if (hs)
     cfgpp_update<true>(mode, k, eu, ec, zv, old_d, zn, z0, no);

@@ -51,7 +51,8 @@ struct StepCoef {  // per-step scalars, computed on the host in fp32 exactly as 
                          // DPM++: c_out(-sigma_i), 1/sigma_i, sigma_{i+1}, unused
   float d0, d1, d2;      // DPM++ 2M branch: -exp(-h), expm1(-h), 1/(2r) ; d3 = exp(-h)
   float d3;
-  int second_order;      // DPM++: 1 -> 2M update, 0 -> Euler-CFG++ update
+  int second_order;      // DPM++ / Euler family bits: 1 = 2M update (else Euler), 2 = extrapolate with the guided
+                         // estimate (plain CFG), 4 = 2M difference term on the guided estimate (SD v1.5 dpm++_2m_cfg++)
 };
 
 // One sampler step's device-resident scalars; a table of these lives in HBM and a 1-thread kernel selects the

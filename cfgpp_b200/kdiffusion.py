@@ -75,6 +75,25 @@ class KDiffusionMixin:
         return self._k_denoise(x, sigma, t, cfg_guidance, (uc, c, add_cond_kwargs))
 
 
+def _fused_trajectory(solver, x, steps, cond):
+    """Whole VE-cast trajectory on the fused step kernel (UNet + CFG / CFG++ mix + Euler / DPM++2M update in the conv_out
+    epilogue, one CUDA-graph replay per step, no elementwise launch or host sync in between). Returns (last denoised, x)."""
+    from . import schedule as S
+    solver._prepare(x, *cond, force=True)
+    eng = solver.unet
+    eng.set_schedule(S.STEP_DPMPP2M_CFGPP, torch.float16, steps)
+    eng.set_state(x)
+    eng.run_steps(0, len(steps))
+    return eng.get_state(1), eng.get_state(0)
+
+
+def _fusable(solver, callback_fn) -> bool:
+    """Deterministic loops without a callback run fused when the solver sits on the native engine (the CPU tests drive
+    these loops with a stand-in UNet and keep the op-by-op torch form, which stays the specification)."""
+    from .engine import NativeUNet
+    return callback_fn is None and isinstance(getattr(solver, "unet", None), NativeUNet)
+
+
 def _callback(callback_fn: Optional[Callable], i, t, z0t, zt, decode):
     if callback_fn is None:
         return z0t, zt
@@ -89,6 +108,9 @@ def euler_cfgpp_loop(solver: KDiffusionMixin, x, sigmas, cfg_guidance, cond, cal
     latent_diffusion.py:699-719 (euler_cfg++), :744-762 (euler_a_cfg++), latent_sdxl.py:787-808 (SDXL euler_cfg++).
     Returns (last denoised, x). `adopt_callback`: the ancestral variant of the reference ignores what the callback
     returns (:757-762). `cfgpp=False`: plain CFG, the derivative uses the guided estimate (:326-330, :372-379)."""
+    if not ancestral and _fusable(solver, callback_fn):
+        from . import schedule as S
+        return _fused_trajectory(solver, x, S.kd_steps(sigmas, solver.timestep, cfg_guidance, cfgpp), cond)
     denoised = None
     for i in range(len(sigmas) - 1):
         sigma = sigmas[i]
@@ -151,6 +173,10 @@ def dpmpp_2m_cfgpp_karras_loop(solver: KDiffusionMixin, x, sigmas, cfg_guidance,
     second-order term uses (denoised - old_denoised) with the GUIDED estimate, SDXL's `dpm++_2m_cfgpp` uses the
     unconditional one (latent_sdxl.py:916; that one runs on the fused step kernel). `cfgpp=False`: plain `dpm++_2m`
     (:470-487), guided estimate everywhere."""
+    if _fusable(solver, callback_fn):
+        from . import schedule as S
+        return _fused_trajectory(solver, x, S.kd_steps(sigmas, solver.timestep, cfg_guidance, cfgpp, second_order=True,
+                                                       diff_guided=True), cond)
     t_fn = lambda s: s.log().neg()  # noqa: E731
     old_denoised = None
     denoised = None

@@ -148,6 +148,36 @@ def dpmpp_2m_cfgpp_steps(sch: Schedule, cfg_guidance: float):
     return out, sigmas[0]
 
 
+KD_SECOND_ORDER, KD_EXTRAP_GUIDED, KD_DIFF_GUIDED = 1, 2, 4   # cfgpp_step_coef.second_order bits
+
+
+def kd_steps(sigmas: torch.Tensor, timestep_fn, cfg_guidance: float, cfgpp: bool, second_order: bool = False,
+             diff_guided: bool = False) -> List[StepStateC]:
+    """Per-step scalars of the VE-cast ("k-diffusion") loops for the fused STEP_DPMPP2M_CFGPP family:
+    Euler (latent_diffusion.py:699-719 / :326-330, latent_sdxl.py:787-808) and the Karras-sigma DPM++(2M) of SD v1.5
+    (:847-877 / :470-487). `sigmas` ends with 0; `timestep_fn(sigma)` is the solver's `timestep()`.
+    The UNet sees x / (sigma^2 + 1)^0.5 (a CPU-scalar divisor = an fp32 reciprocal multiply on CUDA) at t = timestep(sigma);
+    den / ud = x - sigma eps; d = (x - extrap) / sigma.item() (again a reciprocal multiply)."""
+    t_fn = lambda sg: sg.log().neg()  # noqa: E731
+    one = torch.tensor(1.0, dtype=torch.float32)
+    base = 0 if cfgpp else KD_EXTRAP_GUIDED
+    out = []
+    for i in range(len(sigmas) - 1):
+        sigma = sigmas[i]
+        in_scale = one / (sigma ** 2 + 1) ** 0.5
+        inv_sigma = one / torch.tensor(sigma.item(), dtype=torch.float32)
+        t = float(timestep_fn(sigma))
+        c = (-sigma.clone(), inv_sigma, sigmas[i + 1], 0.0)
+        if not second_order or i == 0 or sigmas[i + 1] == 0:
+            out.append(_state(t, in_scale, cfg_guidance, c=c, second_order=base))
+        else:
+            h = t_fn(sigmas[i + 1]) - t_fn(sigmas[i])
+            r = (t_fn(sigmas[i]) - t_fn(sigmas[i - 1])) / h
+            out.append(_state(t, in_scale, cfg_guidance, c=c, d=(-torch.exp(-h), (-h).expm1(), one / (2 * r), torch.exp(-h)),
+                              second_order=base | KD_SECOND_ORDER | (KD_DIFF_GUIDED if diff_guided else 0)))
+    return out
+
+
 def to_c_array(steps: List[StepStateC]):
     arr = (StepStateC * len(steps))()
     for i, s in enumerate(steps):

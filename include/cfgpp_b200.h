@@ -67,7 +67,9 @@ typedef struct cfgpp_step_coef {
                             DDIM-inv: sqrt(1-a_prev), sqrt(a_prev), sqrt(a_t), sqrt(1-a_t)
                             DPM++2M: c_out = -sigma_i, 1/sigma_i, sigma_{i+1}, unused */
   float d0, d1, d2, d3;  /* DPM++2M 2nd-order branch: -exp(-h), expm1(-h), 1/(2r), exp(-h) */
-  int second_order;      /* DPM++2M: 1 = 2M update, 0 = Euler-CFG++ update (first step / sigma_next == 0) */
+  int second_order;      /* VE-cast family bits: 1 = 2M update (else the Euler-CFG++ update: first step / sigma_next == 0 /
+                            euler solvers), 2 = extrapolate with the guided estimate (plain-CFG euler, dpm++_2m),
+                            4 = 2M difference term on the guided estimate (SD v1.5 dpm++_2m_cfg++) */
 } cfgpp_step_coef;
 
 typedef struct cfgpp_step_state {
