@@ -398,3 +398,41 @@ def test_plain_cfg_solvers_vs_oracle():
     _, x = s2.reverse_process(uc, c, lam, x0.clone())
     print(f"sd15 dpm++_2s_a (plain CFG): rel-L2 final x {rel_l2(x, x_ref):.3e}")
     assert rel_l2(x, x_ref) <= 3e-2
+
+
+def test_step_kernel_kdiffusion_family_matches_reference_arithmetic():
+    """The selector bits of the fused VE-cast step (cfgpp_step_coef.second_order): Euler with the unconditional /
+    guided extrapolation (latent_diffusion.py:699-719 / :326-330) and the Karras-sigma DPM++(2M) of SD v1.5 whose
+    difference term uses the GUIDED estimate (:863), CFG++ and plain — against the torch ops of kdiffusion.py on the
+    same eps, <= 2 fp16 ulp per step (teacher-forced)."""
+    from cfgpp_b200 import _native as nv, kdiffusion as K, schedule as S
+    g = torch.Generator().manual_seed(4)
+    sigmas = K.get_sigmas_karras(6, 0.03, 14.6, rho=7.)
+    timestep_fn = lambda s: torch.tensor(500)  # noqa: E731 — irrelevant for the update arithmetic
+    t_fn = lambda s: s.log().neg()  # noqa: E731
+    for cfgpp in (True, False):
+        for second in (False, True):
+            steps = S.kd_steps(sigmas, timestep_fn, 0.6, cfgpp, second_order=second, diff_guided=second)
+            x = (torch.randn(1, 4, 32, 32, generator=g) * sigmas[0]).half().to(dev)
+            xs, aux, old = x.clone(), torch.zeros_like(x), None
+            for i in range(len(sigmas) - 1):
+                eu = torch.randn(1, 4, 32, 32, generator=g).half().to(dev)
+                ec = torch.randn(1, 4, 32, 32, generator=g).half().to(dev)
+                npred = eu + 0.6 * (ec - eu)
+                den, ud = x - npred * sigmas[i], x - eu * sigmas[i]
+                ex = ud if cfgpp else den
+                if not second or old is None or sigmas[i + 1] == 0:
+                    xr = den + (x - ex) / sigmas[i].item() * sigmas[i + 1]
+                else:
+                    h = t_fn(sigmas[i + 1]) - t_fn(sigmas[i])
+                    r = (t_fn(sigmas[i]) - t_fn(sigmas[i - 1])) / h
+                    xr = den + (-torch.exp(-h) * ex - (-h).expm1() * (den - old) / (2 * r)) + torch.exp(-h) * x
+                old = ex
+                z0 = nv.op_cfgpp_step(eu, ec, S.STEP_DPMPP2M_CFGPP, steps[i].coef, xs, aux)
+                tag = f"cfgpp={cfgpp} second={second} step {i}"
+                assert ((xs.float() - xr.float()).abs() <= 2 * _ulp16(xr)).all(), tag
+                assert ((z0.float() - den.float()).abs() <= 1 * _ulp16(den)).all(), tag
+                assert ((aux.float() - ex.float()).abs() <= 1 * _ulp16(ex)).all(), tag
+                x = xr
+                xs.copy_(xr)
+                aux.copy_(ex)
