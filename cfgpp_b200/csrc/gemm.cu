@@ -931,7 +931,7 @@ GemmOp make_conv3x3_op(const __half* x, int B, int H, int W, int Cin, const __ha
   GemmParams& p = op.p;
   CFGPP_REQUIRE(Cin % BK == 0, "conv3x3 Cin must be a multiple of 64");
   CFGPP_REQUIRE(Cout % 8 == 0, "conv3x3 Cout must be a multiple of 8");
-  CFGPP_REQUIRE(conv3x3_geometry_supported(H, W), "conv3x3 needs power-of-two H, W (W <= 128) or W % 128 == 0");
+  CFGPP_REQUIRE(conv3x3_geometry_supported(H, W), "conv3x3 needs W % 128 == 0, or a power-of-two W <= 128 with H a multiple of 128 / W (or H * W dividing 128)");
   const int Wt = W < BM ? W : BM;
   const int Ht = (BM / Wt) < H ? (BM / Wt) : H;
   const int Nt = BM / (Wt * Ht);

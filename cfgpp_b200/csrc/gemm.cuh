@@ -73,12 +73,17 @@ GemmOp make_conv3x3_op(const __half* x, int B, int H, int W, int Cin, const __ha
 
 void run_gemm_op(const GemmOp& op, cudaStream_t stream);
 
-// Geometry the implicit-GEMM A tile (a 4-D TMA box of 128 consecutive output pixels) can address: W <= 128 needs
-// power-of-two H, W (a tile = whole rows, possibly of several images); W > 128 needs W % 128 == 0 (a tile = a row segment).
+// Geometry the implicit-GEMM A tile (a 4-D TMA box of 128 consecutive output pixels) can address:
+//   W > 128           : W % 128 == 0 (a tile = a 128-pixel row segment), any H;
+//   W <= 128, pow2    : a tile = 128 / W whole rows: H must be a multiple of that (e.g. 96 x 128, 48 x 64, 24 x 32 —
+//                       the landscape aspect buckets), or, for images smaller than a tile, H * W must divide 128
+//                       (a tile = several whole images).
 inline bool conv3x3_geometry_supported(int H, int W) {
   if (H < 1 || W < 1) return false;
   if (W > 128) return W % 128 == 0;
-  return (W & (W - 1)) == 0 && (H & (H - 1)) == 0;
+  if ((W & (W - 1)) != 0) return false;
+  const int rows = 128 / W;
+  return H >= rows ? (H % rows == 0) : (128 % (H * W) == 0);
 }
 
 }  // namespace cfgpp

@@ -202,7 +202,7 @@ def test_failed_prepare_forces_replan():
     net.set_prompt(torch.cat([uc, c]), add["text_embeds"], add["time_ids"].float())
     a = net.predict_noise(z, 500.0)
     with pytest.raises(nv.NativeError):
-        net.prepare(1, 24, 24)      # 24 is not a power of two: rejected before anything is freed
+        net.prepare(1, 24, 24)      # width 24 is not a power of two: rejected before anything is freed
     with pytest.raises(nv.NativeError):
         net.prepare(9, 32, 32)      # UNet batch 18 > 16
     net.prepare(1, 32, 32)

@@ -47,6 +47,29 @@ def test_unet_forward_lightning_style_undup_added_cond():
     run_case("tiny_sdxl", 1, 32, 999, dup=False)
 
 
+def test_unet_forward_landscape_latent():
+    """A 4:3 aspect bucket (latent 96 x 128 = 768 x 1024 px): power-of-two width, H a multiple of the rows per conv
+    tile at every level (96x128, 48x64, 24x32) — the reference takes any `shape` (latent_sdxl.py:720)."""
+    from oracle import unet as O
+    cfg, sd, net, ref16 = build_pair("tiny_sdxl", dev)
+    g = torch.Generator().manual_seed(3)
+    B, h, w = 1, 96, 128
+    z = torch.randn(B, 4, h, w, generator=g).to(dev)
+    uc = torch.randn(B, 77, cfg.cross_attention_dim, generator=g).half().to(dev)
+    c = torch.randn(B, 77, cfg.cross_attention_dim, generator=g).half().to(dev)
+    add = {"text_embeds": torch.randn(2 * B, cfg.pooled_dim, generator=g).half().to(dev),
+           "time_ids": torch.tensor([[768., 1024, 0, 0, 768, 1024]] * (2 * B)).half().to(dev)}
+    net.prepare(B, h, w)
+    net.set_prompt(torch.cat([uc, c]), add["text_embeds"], add["time_ids"].float())
+    eu, ec = net.predict_noise(z, 333.0)
+    got = torch.cat([eu, ec]).float()
+    r16 = ref16(torch.cat([z] * 2), torch.tensor(333, device=dev), torch.cat([uc, c]), add)["sample"].float()
+    e = rel_l2(got, r16)
+    print(f"tiny_sdxl 96x128 latent: rel-L2 vs fp16 oracle {e:.3e}")
+    assert got.shape == (2, 4, 96, 128) and e <= TOL
+    net.close()
+
+
 def test_unet_forward_sdxl_full_size():
     """BASELINE config 3 geometry: SDXL, 128x128 latent (1024^2), UNet batch 2 (one image, uncond+cond)."""
     run_case("sdxl", 1, 128, 501)

@@ -56,7 +56,8 @@ def _case(kind, B, h, w, zdtype=torch.float32, seed=5, check32=True):
         assert rel_l2(got[i], r16[i]) <= 5e-3
 
 
-@pytest.mark.parametrize("B,h,w,zdtype", [(1, 16, 16, torch.float32), (2, 32, 32, torch.float16), (3, 16, 32, torch.float32)])
+@pytest.mark.parametrize("B,h,w,zdtype", [(1, 16, 16, torch.float32), (2, 32, 32, torch.float16), (3, 16, 32, torch.float32),
+                                          (1, 24, 32, torch.float32)])
 def test_vae_decode_tiny(B, h, w, zdtype):
     _case("tiny_vae", B, h, w, zdtype)
 
