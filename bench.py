@@ -62,6 +62,25 @@ def log(msg):
     print(f"[bench] {msg}", file=sys.stderr, flush=True)
 
 
+# stdout carries exactly ONE line — the JSON record. Libraries write there too (NCCL prints its version banner on fd 1
+# from C), so fd 1 is pointed at stderr for the whole run and the record goes to a saved copy of the real stdout.
+_REAL_STDOUT = None
+
+
+def _capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -306,7 +325,7 @@ def run_reference_arm(args, wl):
                        "parallelism": f"dp{args.gpus}"},
             "cpu_baseline": r,
             "e2e": {"value": r["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -323,8 +342,6 @@ def run_ours(args, wl):
         raise SystemExit("bench.py (ours) needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line (NCCL prints its version banner there)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -486,7 +503,7 @@ def run_ours(args, wl):
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"error": repr(e)[:200], "value": None, "unit": "images/sec",
                                     "cores": len(os.sched_getaffinity(0)), "kind": "port", "sample": "failed"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -544,6 +561,7 @@ def main():
     ap.add_argument("--config", type=str, default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-baselines", action="store_true", help="skip the GPU-eager and CPU baselines at N=1")
     args = ap.parse_args()
+    _capture_stdout()
     wl = WORKLOADS[args.config]
     if args.impl == "reference":
         run_reference_arm(args, wl)
