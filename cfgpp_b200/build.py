@@ -58,8 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         objs = list(ex.map(lambda s: _compile(s, force, hdr_mtime, verbose), srcs))
     newest = max(o.stat().st_mtime for o in objs)
     if force or not LIB.exists() or LIB.stat().st_mtime < newest:
-        cmd = [NVCC, *ARCH, "-shared", "-o", str(LIB), *map(str, objs), "-lnccl_static_placeholder"]
-        cmd = [c for c in cmd if c != "-lnccl_static_placeholder"]
+        cmd = [NVCC, *ARCH, "-shared", "-o", str(LIB), *map(str, objs)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

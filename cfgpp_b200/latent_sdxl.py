@@ -289,9 +289,7 @@ class SDXL(K.KDiffusionMixin):
 
     def sigma_to_t(self, sigma, quantize=None):
         quantize = self.quantize if quantize is None else quantize
-        if not quantize:
-            raise NotImplementedError("only the quantized sigma_to_t is used by the CFG++ solvers")
-        return S.sigma_to_t(self._sch, sigma)
+        return S.sigma_to_t(self._sch, sigma, quantize)
 
     # ---- shared trajectory driver -------------------------------------------------------------------------------
     def _run_trajectory(self, method, state_dtype, steps, z_init, uc, c, add_cond_kwargs, callback_fn, result):

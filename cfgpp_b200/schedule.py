@@ -116,11 +116,19 @@ def ddim_inversion_cfgpp_steps(sch: Schedule, cfg_guidance: float) -> List[StepS
     return out
 
 
-def sigma_to_t(sch: Schedule, sigma: torch.Tensor) -> torch.Tensor:
-    """SDXL.sigma_to_t, quantize=True (latent_sdxl.py:333-339)."""
+def sigma_to_t(sch: Schedule, sigma: torch.Tensor, quantize: bool = True) -> torch.Tensor:
+    """SDXL.sigma_to_t (latent_sdxl.py:333-346, "taken from k_diffusion/external.py"): nearest index in the un-shifted
+    sigma table (quantize=True, what the CFG++ solvers use) or the linearly interpolated fractional index."""
     total_sigmas = (1 - sch.total_alphas).sqrt() / sch.total_alphas.sqrt()
     dists = sigma - total_sigmas[:, None]
-    return dists.abs().argmin(dim=0).view(sigma.shape)
+    if quantize:
+        return dists.abs().argmin(dim=0).view(sigma.shape)
+    low_idx = dists.ge(0).cumsum(dim=0).argmax(dim=0).clamp(max=total_sigmas.shape[0] - 2)
+    high_idx = low_idx + 1
+    low, high = total_sigmas[low_idx], total_sigmas[high_idx]
+    w = ((low - sigma) / (low - high)).clamp(0, 1)
+    t = (1 - w) * low_idx + w * high_idx
+    return t.view(sigma.shape)
 
 
 def dpmpp_2m_cfgpp_steps(sch: Schedule, cfg_guidance: float):

@@ -11,7 +11,7 @@ quirks of SURVEY.md Appendix C) kept line for line:
   SDXL     dpm++_2m_cfgpp       latent_sdxl.py:860-930 (sigma_to_t :333-346, to_d :353-355)
 
 PARITY UNPINNED: the reference has no tests / golden vectors and cannot be imported here (diffusers is
-absent), so these loops are pinned only by the algebraic identities in tests/test_oracle_samplers.py
+absent), so these loops are pinned only by the algebraic identities in tests/test_oracle.py and the golden vectors
 (lambda=0 => unconditional DDIM; eps_uc == eps_c => CFG++ == DDIM; inversion step inverts the sampling step;
 DPM++2M first step == Euler-CFG++).
 

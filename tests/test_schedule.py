@@ -74,3 +74,17 @@ def test_ddim_step_tables_match_reference_indexing():
     inv = PS.ddim_inversion_cfgpp_steps(sch, 0.6)
     assert int(inv[0].t) == 1 and int(inv[-1].t) == 981
     assert close(inv[0].coef.c1, sch.final_alpha_cumprod.sqrt()) and close(inv[0].coef.c2, acp[1].sqrt())
+
+
+def test_sigma_to_t_quantized_and_interpolated():
+    """latent_sdxl.py:333-346: nearest table index, or the fractional index between the two bracketing sigmas."""
+    from cfgpp_b200 import schedule as S
+    sch = S.Schedule.make(50)
+    ts = (1 - sch.total_alphas).sqrt() / sch.total_alphas.sqrt()
+    exact = ts[[3, 500, 998]]
+    assert S.sigma_to_t(sch, exact).tolist() == [3, 500, 998]
+    assert torch.allclose(S.sigma_to_t(sch, exact, quantize=False), torch.tensor([3., 500., 998.]), atol=1e-3)
+    mid = (ts[200] + ts[201]) / 2
+    t = S.sigma_to_t(sch, mid[None], quantize=False)
+    assert 200.0 < t.item() < 201.0 and abs(t.item() - 200.5) < 0.05
+    assert S.sigma_to_t(sch, torch.tensor([1e6]), quantize=False).item() == 999.0   # clamped above the table
