@@ -42,6 +42,7 @@ constexpr int ATOM_BYTES = 128 * 64 * 2;  // 16 KB: one [128 rows x 64 fp16] swi
 constexpr int kThreads = 384;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
+constexpr int kDefaultPoly = 0;            // see attn_poly()
 
 // HD = padded head dim (64 / 128 / 192: heads of 40 / 80 / 160 channels are zero-padded by the QKV projection),
 // NQT = query tiles per CTA, KS = K / V ring depth. TMEM: S_q at [q*128], O_q at [NQT*128 + q*HD].
@@ -56,7 +57,8 @@ struct ACfg {
   static_assert(SMEM_BYTES <= 232448, "shared memory overflow");
 };
 
-template <int HD, int NQT, int KS>
+// POLY: 0 = every exponential on the MUFU pipe; n > 0 = every n-th one through exp2_poly() on the FMA pipe
+template <int HD, int NQT, int KS, int POLY>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
             const __grid_constant__ CUtensorMap map_v) {
@@ -241,13 +243,17 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
           for (int i = 0; i < 128; ++i)
             if (i >= valid) s[i] = 0xff800000u;  // -inf
         }
-        float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
+        // row maximum: eight independent chains of three-input maxima (two dependent chains of 63 two-input ones
+        // cost ~250 cycles of pure latency per tile)
+        float mxc[8];
 #pragma unroll
-        for (int i = 2; i < 128; i += 2) {
-          mx0 = fmaxf(mx0, __uint_as_float(s[i]));
-          mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+        for (int k8 = 0; k8 < 8; ++k8) mxc[k8] = fmaxf(__uint_as_float(s[k8]), __uint_as_float(s[8 + k8]));
+#pragma unroll
+        for (int i = 16; i < 128; i += 16) {
+#pragma unroll
+          for (int k8 = 0; k8 < 8; ++k8) mxc[k8] = fmax3(mxc[k8], __uint_as_float(s[i + k8]), __uint_as_float(s[i + 8 + k8]));
         }
-        const float mx = fmaxf(mx0, mx1);
+        const float mx = fmax3(fmax3(mxc[0], mxc[1], mxc[2]), fmax3(mxc[3], mxc[4], mxc[5]), fmaxf(mxc[6], mxc[7]));
         // lazy running max: move the reference only when it would otherwise overflow the comfortable range
         float alpha = 1.0f;
         bool need = false;
@@ -282,8 +288,14 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
           uint32_t pk[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float p0 = fast_exp2(__uint_as_float(s[g * 8 + 2 * e]) * c - mc);
-            const float p1 = fast_exp2(__uint_as_float(s[g * 8 + 2 * e + 1]) * c - mc);
+            const float x0 = __uint_as_float(s[g * 8 + 2 * e]) * c - mc;
+            const float x1 = __uint_as_float(s[g * 8 + 2 * e + 1]) * c - mc;
+            // (g, e are unrolled: the selection folds at compile time)
+            constexpr int kP = POLY > 0 ? POLY : 1;
+            const bool poly0 = POLY > 0 && ((g * 8 + 2 * e) % kP) == kP - 1;
+            const bool poly1 = POLY > 0 && ((g * 8 + 2 * e + 1) % kP) == kP - 1;
+            const float p0 = poly0 ? exp2_poly(x0) : fast_exp2(x0);
+            const float p1 = poly1 ? exp2_poly(x1) : fast_exp2(x1);
             rs0 += p0;
             rs1 += p1;
             pk[e] = pack_half2(p0, p1);
@@ -337,17 +349,28 @@ CUtensorMap make_head_map(const __half* base, int ld, int B, int N, int cols) {
   return make_tmap_f16(base, 3, dims, strides, box);
 }
 
-template <int HD, int NQT, int KS>
+template <int HD, int NQT, int KS, int POLY = 0>
 void configure_one() {
-  CFGPP_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel<HD, NQT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CFGPP_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel<HD, NQT, KS, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         ACfg<HD, NQT, KS>::SMEM_BYTES));
 }
 
-template <int HD, int NQT, int KS>
+template <int HD, int NQT, int KS, int POLY = 0>
 void launch(const AttnOp& op, cudaStream_t stream) {
   dim3 grid((op.p.Nq + NQT * BQ - 1) / (NQT * BQ), op.p.H, op.p.B);
-  launch_pdl(attn_kernel<HD, NQT, KS>, grid, dim3(kThreads), ACfg<HD, NQT, KS>::SMEM_BYTES, stream, op.p, op.map_q,
+  launch_pdl(attn_kernel<HD, NQT, KS, POLY>, grid, dim3(kThreads), ACfg<HD, NQT, KS>::SMEM_BYTES, stream, op.p, op.map_q,
              op.map_k, op.map_v);
+}
+
+// fraction of the exponentials computed on the FMA pipe for head dim 64: CFGPP_ATTN_POLY = 0 (none), 8, 4 or 3 (every n-th)
+int attn_poly() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("CFGPP_ATTN_POLY");
+    v = e ? atoi(e) : kDefaultPoly;
+    if (v != 0 && v != 8 && v != 4 && v != 3) v = kDefaultPoly;
+  }
+  return v;
 }
 
 }  // namespace
@@ -375,6 +398,9 @@ void attn_configure() {
   static bool done = false;
   if (done) return;
   configure_one<64, 2, 3>();
+  configure_one<64, 2, 3, 8>();
+  configure_one<64, 2, 3, 4>();
+  configure_one<64, 2, 3, 3>();
   configure_one<128, 1, 2>();
   configure_one<192, 1, 1>();
   xattn_configure();
@@ -402,7 +428,13 @@ void run_attn_op(const AttnOp& op, cudaStream_t stream) {
   if (use_p && attn_persist_applicable(op)) return run_attn_persist_op(op, stream);
   attn_configure();
   switch (op.hd_pad) {
-    case 64: return launch<64, 2, 3>(op, stream);
+    case 64:
+      switch (attn_poly()) {
+        case 8: return launch<64, 2, 3, 8>(op, stream);
+        case 4: return launch<64, 2, 3, 4>(op, stream);
+        case 3: return launch<64, 2, 3, 3>(op, stream);
+        default: return launch<64, 2, 3>(op, stream);
+      }
     case 128: return launch<128, 1, 2>(op, stream);
     case 192: return launch<192, 1, 1>(op, stream);
     default: throw Error(-1, "unsupported padded head dim");

@@ -374,6 +374,27 @@ CFGPP_DEVICE float fast_exp2(float x) {
   return y;
 }
 
+// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + r, r in [-0.5, 0.5], degree-3 minimax polynomial
+// for 2^r (max relative error 7.5e-5, a sixth of an fp16 ulp), n added into the exponent field. Valid for x <= ~100;
+// x below -126 (incl. -inf from masking) flushes to ~1e-38. Used for a fraction of the softmax exponentials: the
+// attention kernels are bound by the 16 ex2 / clk / SM of the MUFU pipe, not by the tensor pipe (FA4's trick).
+CFGPP_DEVICE float exp2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;  // 1.5 * 2^23: the integer nearest to x lands in the low mantissa bits
+  const float r = x - (t - 12582912.0f);
+  float p = 0.0551716648042202f;
+  p = fmaf(p, r, 0.2426111251115799f);
+  p = fmaf(p, r, 0.6932609677314758f);
+  p = fmaf(p, r, 0.9999280571937561f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+// three-input maximum (FMNMX3 on sm_100)
+CFGPP_DEVICE float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
 CFGPP_DEVICE uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
