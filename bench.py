@@ -473,6 +473,28 @@ def run_ours(args, wl):
                               "once_per_prompt": stats["prompt_flops"] / 1e12,
                               "algorithmic_per_step": eng.forward_flops / 1e12}}
 
+    # ---- VAE decode of one batch of final latents (outside the metric; the step after the path) --------
+    try:
+        dec = getattr(getattr(solver, "vae", None), "decoder", None)
+        if dec is not None:
+            zfin = trajectory_device(args.warmup)
+            dec.decode_fp16(zfin)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                dec.decode_fp16(zfin)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            st = dec.stats
+            line["vae_decode"] = {"ms_per_batch": ms, "images": BATCH, "tflops": st["flops"] / (ms / 1e3) / 1e12,
+                                  "share_of_trajectory": ms / (ms_dev / args.steps),
+                                  "what": "native AutoencoderKL decoder (cfgpp_vae_decode), device-timed, not part of `value`"}
+            del dec, zfin
+    except Exception as e:  # noqa: BLE001 — never lose the measured line to an optional leg
+        line["vae_decode"] = {"error": repr(e)[:200]}
+
     def checkpoint_line():
         s = json.dumps(line)
         print("[bench partial] " + s, file=sys.stderr, flush=True)
