@@ -43,26 +43,32 @@ constexpr int kThreads = 384;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 constexpr int kDefaultPoly = 0;            // see attn_poly()
+constexpr int kDefaultRowsumMma = 0;       // see attn_rowsum_mma()
 
 // HD = padded head dim (64 / 128 / 192: heads of 40 / 80 / 160 channels are zero-padded by the QKV projection),
 // NQT = query tiles per CTA, KS = K / V ring depth. TMEM: S_q at [q*128], O_q at [NQT*128 + q*HD].
-template <int HD, int NQT, int KS>
+// RS: the softmax row sums come out of the P V tensor-core product (a constant "ones" column appended to V: O gets 16
+// extra columns, column HD = sum_j fp16(p_j)) instead of 128 FADDs per thread and tile.
+template <int HD, int NQT, int KS, bool RS = false>
 struct ACfg {
   static constexpr int NA = HD / 64;                    // swizzle atoms per tile row
   static constexpr int TILE_BYTES = NA * ATOM_BYTES;    // one Q / K / V tile
   static constexpr int P_BYTES = 2 * ATOM_BYTES;        // one P tile (128 x 128 fp16)
-  static constexpr int SMEM_BYTES = TILE_BYTES * (NQT + 2 * KS) + P_BYTES * NQT + 1024 + 256;
+  static constexpr int OW = HD + (RS ? 16 : 0);        // accumulator columns per query tile
+  static constexpr int SMEM_BYTES = TILE_BYTES * (NQT + 2 * KS) + P_BYTES * NQT + (RS ? ATOM_BYTES : 0) + 1024 + 256;
   static constexpr uint32_t O_COL = NQT * 128;
-  static_assert(NQT * 128 + NQT * HD <= 512, "TMEM overflow");
+  static_assert(!RS || HD == 64, "the ones column is implemented for head dim 64");
+  static_assert(NQT * 128 + NQT * OW <= 512, "TMEM overflow");
   static_assert(SMEM_BYTES <= 232448, "shared memory overflow");
 };
 
 // POLY: 0 = every exponential on the MUFU pipe; n > 0 = every n-th one through exp2_poly() on the FMA pipe
-template <int HD, int NQT, int KS, int POLY>
+template <int HD, int NQT, int KS, int POLY, bool RS>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
             const __grid_constant__ CUtensorMap map_v) {
-  using A = ACfg<HD, NQT, KS>;
+  using A = ACfg<HD, NQT, KS, RS>;
+  constexpr int OW = A::OW;
   constexpr int TILE_BYTES = A::TILE_BYTES;
   constexpr int NA = A::NA;
   constexpr uint32_t O_COL = A::O_COL;
@@ -73,7 +79,8 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
   uint8_t* sK = sQ + NQT * TILE_BYTES;     // KS tiles
   uint8_t* sV = sK + KS * TILE_BYTES;      // KS tiles
   uint8_t* sP = sV + KS * TILE_BYTES;      // NQT query tiles x 2 halves of 64 columns
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NQT * A::P_BYTES);
+  uint8_t* sOnes = sP + NQT * A::P_BYTES;  // RS: [128 kv rows x 64] fp16 MN-major atom whose column 0 is 1.0
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + (RS ? ATOM_BYTES : 0));
   uint64_t* q_full = bars;            // [2]
   uint64_t* k_full = q_full + 2;      // [KS]
   uint64_t* k_empty = k_full + KS;
@@ -118,6 +125,16 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
     tmem_alloc(tmem_ptr_smem, TMEM_COLS);
     tmem_relinquish();
   }
+  if constexpr (RS) {
+    if (warp_idx == 3) {  // row k: element (k, 0) = 1.0, the 16-byte chunk holding it sits at chunk (0 ^ (k & 7)) (128B swizzle)
+      for (int k = lane; k < 128; k += 32) {
+        uint4* rowp = reinterpret_cast<uint4*>(sOnes + k * 128);
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) rowp[ch] = make_uint4(ch == (k & 7) ? 0x00003C00u : 0u, 0u, 0u, 0u);
+      }
+      fence_proxy_async_smem();
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -151,7 +168,7 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
     if (lane == 0) {
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc_qk = make_idesc_f16(128, BKV, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_f16(128, HD, 0, 1);  // B (= V) is MN-major
+      constexpr uint32_t idesc_pv = make_idesc_f16(128, OW, 0, 1);  // B (= V [+ ones column]) is MN-major
       auto issue_qk = [&](int qt, int j) {
 #pragma unroll
         for (int a = 0; a < NA; ++a) {  // K dimension = head dim: one 64-wide swizzle atom at a time
@@ -166,12 +183,14 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
       auto issue_pv = [&](int qt, int j) {
         // V tile: 128 kv rows x HD d as NA atoms of [128 rows x 64 d] (128 B per row, swizzled) = MN-major B operand:
         // 8-row K groups are 1024 B apart (SBO), 64-wide N atoms 16 KB apart (LBO); a K step of 16 rows advances 2048 B.
-        const uint64_t v_desc = make_sdesc_sw128(smem_u32(sV + (j % KS) * TILE_BYTES), 1024, ATOM_BYTES);
+        // (RS: the second 64-wide N atom is the constant ones tile, reached through the leading-dimension byte offset)
+        const uint32_t v_addr = smem_u32(sV + (j % KS) * TILE_BYTES);
+        const uint64_t v_desc = make_sdesc_sw128(v_addr, 1024, RS ? (smem_u32(sOnes) - v_addr) : ATOM_BYTES);
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
           const uint64_t p_desc =
               make_sdesc_sw128(smem_u32(sP + qt * A::P_BYTES + (k >> 2) * ATOM_BYTES), 1024, 0) + 2 * (k & 3);
-          umma_f16(tmem_base + O_COL + qt * HD, p_desc, v_desc + 128 * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
+          umma_f16(tmem_base + O_COL + qt * OW, p_desc, v_desc + 128 * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
         }
         umma_commit(&pv_done[qt]);
       };
@@ -223,7 +242,7 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
       const int row = qw * 32 + lane;
       const uint32_t lane_off = static_cast<uint32_t>(qw * 32) << 16;
       const uint32_t s_addr = tmem_base + qt * BKV + lane_off;
-      const uint32_t o_addr = tmem_base + O_COL + qt * HD + lane_off;
+      const uint32_t o_addr = tmem_base + O_COL + qt * OW + lane_off;
       uint8_t* prow = sP + qt * A::P_BYTES + row * 128;
       const float c = p.scale_log2e;
       float m_ref = -INFINITY, l_run = 0.f;
@@ -269,7 +288,7 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
           tc_fence_after();
           if (__any_sync(0xffffffffu, need)) {
 #pragma unroll 1
-            for (int h = 0; h < HD / 16; ++h) {  // 16 columns at a time: the 128 scores stay live in registers
+            for (int h = 0; h < OW / 16; ++h) {  // 16 columns at a time: the 128 scores stay live in registers
               uint32_t o[16];
               tmem_ld_x16(o_addr + h * 16, o);
               tmem_ld_wait();
@@ -296,8 +315,10 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
             const bool poly1 = POLY > 0 && ((g * 8 + 2 * e + 1) % kP) == kP - 1;
             const float p0 = poly0 ? exp2_poly(x0) : fast_exp2(x0);
             const float p1 = poly1 ? exp2_poly(x1) : fast_exp2(x1);
-            rs0 += p0;
-            rs1 += p1;
+            if constexpr (!RS) {
+              rs0 += p0;
+              rs1 += p1;
+            }
             pk[e] = pack_half2(p0, p1);
           }
           const int half_idx = g >> 3;        // which 64-column half
@@ -311,6 +332,12 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
       }
       mbar_wait(&pv_done[qt], (n_tiles - 1) & 1);
       tc_fence_after();
+      if constexpr (RS) {  // column HD of the accumulator = sum of the fp16-rounded P over all KV tiles
+        uint32_t lcol[16];
+        tmem_ld_x16(o_addr + HD, lcol);
+        tmem_ld_wait();
+        l_run = __uint_as_float(lcol[0]);
+      }
       const float inv_l = 1.0f / l_run;
       const int qrow = q0 + qt * BQ + row;
       __half* dst = p.out + (static_cast<size_t>(batch) * p.Nq + qrow) * p.ldo + head * HD;
@@ -349,17 +376,27 @@ CUtensorMap make_head_map(const __half* base, int ld, int B, int N, int cols) {
   return make_tmap_f16(base, 3, dims, strides, box);
 }
 
-template <int HD, int NQT, int KS, int POLY = 0>
+template <int HD, int NQT, int KS, int POLY = 0, bool RS = false>
 void configure_one() {
-  CFGPP_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel<HD, NQT, KS, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        ACfg<HD, NQT, KS>::SMEM_BYTES));
+  CFGPP_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel<HD, NQT, KS, POLY, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        ACfg<HD, NQT, KS, RS>::SMEM_BYTES));
 }
 
-template <int HD, int NQT, int KS, int POLY = 0>
+template <int HD, int NQT, int KS, int POLY = 0, bool RS = false>
 void launch(const AttnOp& op, cudaStream_t stream) {
   dim3 grid((op.p.Nq + NQT * BQ - 1) / (NQT * BQ), op.p.H, op.p.B);
-  launch_pdl(attn_kernel<HD, NQT, KS, POLY>, grid, dim3(kThreads), ACfg<HD, NQT, KS>::SMEM_BYTES, stream, op.p, op.map_q,
-             op.map_k, op.map_v);
+  launch_pdl(attn_kernel<HD, NQT, KS, POLY, RS>, grid, dim3(kThreads), ACfg<HD, NQT, KS, RS>::SMEM_BYTES, stream, op.p,
+             op.map_q, op.map_k, op.map_v);
+}
+
+// CFGPP_ATTN_ROWSUM_MMA=1|0: row sums from the tensor pipe (ones column appended to V) for head dim 64
+bool attn_rowsum_mma() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("CFGPP_ATTN_ROWSUM_MMA");
+    v = e ? (e[0] == '1' ? 1 : 0) : kDefaultRowsumMma;
+  }
+  return v == 1;
 }
 
 // fraction of the exponentials computed on the FMA pipe for head dim 64: CFGPP_ATTN_POLY = 0 (none), 8, 4 or 3 (every n-th)
@@ -401,6 +438,7 @@ void attn_configure() {
   configure_one<64, 2, 3, 8>();
   configure_one<64, 2, 3, 4>();
   configure_one<64, 2, 3, 3>();
+  configure_one<64, 2, 3, 0, true>();
   configure_one<128, 1, 2>();
   configure_one<192, 1, 1>();
   xattn_configure();
@@ -429,6 +467,7 @@ void run_attn_op(const AttnOp& op, cudaStream_t stream) {
   attn_configure();
   switch (op.hd_pad) {
     case 64:
+      if (attn_rowsum_mma()) return launch<64, 2, 3, 0, true>(op, stream);
       switch (attn_poly()) {
         case 8: return launch<64, 2, 3, 8>(op, stream);
         case 4: return launch<64, 2, 3, 4>(op, stream);
