@@ -44,18 +44,22 @@ constexpr uint32_t TMEM_COLS = 512;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 constexpr int kDefaultPoly = 0;            // see attn_poly()
 constexpr int kDefaultRowsumMma = 0;       // see attn_rowsum_mma()
+constexpr int kDefaultPbuf = 1;            // see attn_pbuf()
 
 // HD = padded head dim (64 / 128 / 192: heads of 40 / 80 / 160 channels are zero-padded by the QKV projection),
 // NQT = query tiles per CTA, KS = K / V ring depth. TMEM: S_q at [q*128], O_q at [NQT*128 + q*HD].
 // RS: the softmax row sums come out of the P V tensor-core product (a constant "ones" column appended to V: O gets 16
 // extra columns, column HD = sum_j fp16(p_j)) instead of 128 FADDs per thread and tile.
-template <int HD, int NQT, int KS, bool RS = false>
+// PB: P buffers per query tile. With one buffer the softmax of KV tile j+1 must wait for PV(j) to retire before it may
+// write P (a 0.3-0.6 us bubble on every step: issue poll + 8 MMAs + commit); with two it only waits for PV(j-1).
+template <int HD, int NQT, int KS, bool RS = false, int PB = 1>
 struct ACfg {
   static constexpr int NA = HD / 64;                    // swizzle atoms per tile row
   static constexpr int TILE_BYTES = NA * ATOM_BYTES;    // one Q / K / V tile
   static constexpr int P_BYTES = 2 * ATOM_BYTES;        // one P tile (128 x 128 fp16)
   static constexpr int OW = HD + (RS ? 16 : 0);        // accumulator columns per query tile
-  static constexpr int SMEM_BYTES = TILE_BYTES * (NQT + 2 * KS) + P_BYTES * NQT + (RS ? ATOM_BYTES : 0) + 1024 + 256;
+  static constexpr int SMEM_BYTES =
+      TILE_BYTES * (NQT + 2 * KS) + P_BYTES * NQT * PB + (RS ? ATOM_BYTES : 0) + 1024 + 256;
   static constexpr uint32_t O_COL = NQT * 128;
   static_assert(!RS || HD == 64, "the ones column is implemented for head dim 64");
   static_assert(NQT * 128 + NQT * OW <= 512, "TMEM overflow");
@@ -63,11 +67,11 @@ struct ACfg {
 };
 
 // POLY: 0 = every exponential on the MUFU pipe; n > 0 = every n-th one through exp2_poly() on the FMA pipe
-template <int HD, int NQT, int KS, int POLY, bool RS>
+template <int HD, int NQT, int KS, int POLY, bool RS, int PB>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
             const __grid_constant__ CUtensorMap map_v) {
-  using A = ACfg<HD, NQT, KS, RS>;
+  using A = ACfg<HD, NQT, KS, RS, PB>;
   constexpr int OW = A::OW;
   constexpr int TILE_BYTES = A::TILE_BYTES;
   constexpr int NA = A::NA;
@@ -78,8 +82,8 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
   uint8_t* sQ = smem;                      // NQT tiles
   uint8_t* sK = sQ + NQT * TILE_BYTES;     // KS tiles
   uint8_t* sV = sK + KS * TILE_BYTES;      // KS tiles
-  uint8_t* sP = sV + KS * TILE_BYTES;      // NQT query tiles x 2 halves of 64 columns
-  uint8_t* sOnes = sP + NQT * A::P_BYTES;  // RS: [128 kv rows x 64] fp16 MN-major atom whose column 0 is 1.0
+  uint8_t* sP = sV + KS * TILE_BYTES;      // NQT query tiles x PB buffers x 2 halves of 64 columns
+  uint8_t* sOnes = sP + NQT * PB * A::P_BYTES;  // RS: [128 kv rows x 64] fp16 MN-major atom whose column 0 is 1.0
   uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + (RS ? ATOM_BYTES : 0));
   uint64_t* q_full = bars;            // [2]
   uint64_t* k_full = q_full + 2;      // [KS]
@@ -88,9 +92,9 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
   uint64_t* v_empty = v_full + KS;
   uint64_t* s_full = v_empty + KS;    // [2]
   uint64_t* s_free = s_full + 2;      // [2]
-  uint64_t* p_full = s_free + 2;      // [2]
-  uint64_t* pv_done = p_full + 2;     // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* p_full = s_free + 2;      // [2][PB]: one barrier per P buffer (a buffer's phases cannot alias)
+  uint64_t* pv_done = p_full + 2 * PB;  // [2][PB]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pv_done + 2 * PB);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -110,8 +114,10 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
       mbar_init(&q_full[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&s_free[i], 128);
-      mbar_init(&p_full[i], 128);
-      mbar_init(&pv_done[i], 1);
+      for (int b = 0; b < PB; ++b) {
+        mbar_init(&p_full[i * PB + b], 128);
+        mbar_init(&pv_done[i * PB + b], 1);
+      }
     }
     for (int i = 0; i < KS; ++i) {
       mbar_init(&k_full[i], 1);
@@ -186,13 +192,13 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
         // (RS: the second 64-wide N atom is the constant ones tile, reached through the leading-dimension byte offset)
         const uint32_t v_addr = smem_u32(sV + (j % KS) * TILE_BYTES);
         const uint64_t v_desc = make_sdesc_sw128(v_addr, 1024, RS ? (smem_u32(sOnes) - v_addr) : ATOM_BYTES);
+        const uint8_t* pbuf = sP + (qt * PB + (j % PB)) * A::P_BYTES;
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
-          const uint64_t p_desc =
-              make_sdesc_sw128(smem_u32(sP + qt * A::P_BYTES + (k >> 2) * ATOM_BYTES), 1024, 0) + 2 * (k & 3);
+          const uint64_t p_desc = make_sdesc_sw128(smem_u32(pbuf + (k >> 2) * ATOM_BYTES), 1024, 0) + 2 * (k & 3);
           umma_f16(tmem_base + O_COL + qt * OW, p_desc, v_desc + 128 * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&pv_done[qt]);
+        umma_commit(&pv_done[qt * PB + (j % PB)]);
       };
       for (int qt = 0; qt < n_qt; ++qt) mbar_wait(&q_full[qt], 0);
       mbar_wait(&k_full[0], 0);
@@ -208,7 +214,8 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
         bool progressed = false;
         for (int qt = 0; qt < n_qt; ++qt) {
           int j = next_pv[qt];
-          if (j < n_tiles && mbar_try_wait(&p_full[qt], j & 1) && mbar_try_wait(&v_full[j % KS], (j / KS) & 1)) {
+          if (j < n_tiles && mbar_try_wait(&p_full[qt * PB + (j % PB)], (j / PB) & 1) &&
+              mbar_try_wait(&v_full[j % KS], (j / KS) & 1)) {
             tc_fence_after();
             issue_pv(qt, j);
             umma_commit(&v_empty[j % KS]);
@@ -243,7 +250,7 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
       const uint32_t lane_off = static_cast<uint32_t>(qw * 32) << 16;
       const uint32_t s_addr = tmem_base + qt * BKV + lane_off;
       const uint32_t o_addr = tmem_base + O_COL + qt * OW + lane_off;
-      uint8_t* prow = sP + qt * A::P_BYTES + row * 128;
+      uint8_t* prow0 = sP + qt * PB * A::P_BYTES + row * 128;
       const float c = p.scale_log2e;
       float m_ref = -INFINITY, l_run = 0.f;
 
@@ -283,22 +290,27 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
           m_ref = mx;
           need = true;
         }
-        if (j > 0) {
-          mbar_wait(&pv_done[qt], (j - 1) & 1);  // PV_q(j-1) retired: P buffer reusable, O_q rescalable
+        uint8_t* prow = prow0 + (j % PB) * A::P_BYTES;
+        if (j >= PB) {  // PV_q(j-PB) retired: its P buffer is reusable
+          mbar_wait(&pv_done[qt * PB + (j % PB)], ((j - PB) / PB) & 1);
           tc_fence_after();
-          if (__any_sync(0xffffffffu, need)) {
-#pragma unroll 1
-            for (int h = 0; h < OW / 16; ++h) {  // 16 columns at a time: the 128 scores stay live in registers
-              uint32_t o[16];
-              tmem_ld_x16(o_addr + h * 16, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int d = 0; d < 16; ++d) o[d] = __float_as_uint(__uint_as_float(o[d]) * alpha);
-              tmem_st_x16(o_addr + h * 16, o);
-            }
-            tmem_st_wait();
-            l_run *= alpha;
+        }
+        if (j > 0 && __any_sync(0xffffffffu, need)) {
+          if constexpr (PB > 1) {  // O_q is only rescalable once EVERY earlier PV has retired (in-order: the latest)
+            mbar_wait(&pv_done[qt * PB + ((j - 1) % PB)], ((j - 1) / PB) & 1);
+            tc_fence_after();
           }
+#pragma unroll 1
+          for (int h = 0; h < OW / 16; ++h) {  // 16 columns at a time: the 128 scores stay live in registers
+            uint32_t o[16];
+            tmem_ld_x16(o_addr + h * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < 16; ++d) o[d] = __float_as_uint(__uint_as_float(o[d]) * alpha);
+            tmem_st_x16(o_addr + h * 16, o);
+          }
+          tmem_st_wait();
+          l_run *= alpha;
         }
         const float mc = m_ref * c;
         float rs0 = 0.f, rs1 = 0.f;
@@ -328,9 +340,9 @@ attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_q, const
         l_run += rs0 + rs1;
         tc_fence_before();
         fence_proxy_async_smem();
-        mbar_arrive(&p_full[qt]);
+        mbar_arrive(&p_full[qt * PB + (j % PB)]);
       }
-      mbar_wait(&pv_done[qt], (n_tiles - 1) & 1);
+      mbar_wait(&pv_done[qt * PB + ((n_tiles - 1) % PB)], ((n_tiles - 1) / PB) & 1);
       tc_fence_after();
       if constexpr (RS) {  // column HD of the accumulator = sum of the fp16-rounded P over all KV tiles
         uint32_t lcol[16];
@@ -376,17 +388,29 @@ CUtensorMap make_head_map(const __half* base, int ld, int B, int N, int cols) {
   return make_tmap_f16(base, 3, dims, strides, box);
 }
 
-template <int HD, int NQT, int KS, int POLY = 0, bool RS = false>
+template <int HD, int NQT, int KS, int POLY = 0, bool RS = false, int PB = 1>
 void configure_one() {
-  CFGPP_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel<HD, NQT, KS, POLY, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        ACfg<HD, NQT, KS, RS>::SMEM_BYTES));
+  CFGPP_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel<HD, NQT, KS, POLY, RS, PB>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        ACfg<HD, NQT, KS, RS, PB>::SMEM_BYTES));
 }
 
-template <int HD, int NQT, int KS, int POLY = 0, bool RS = false>
+template <int HD, int NQT, int KS, int POLY = 0, bool RS = false, int PB = 1>
 void launch(const AttnOp& op, cudaStream_t stream) {
   dim3 grid((op.p.Nq + NQT * BQ - 1) / (NQT * BQ), op.p.H, op.p.B);
-  launch_pdl(attn_kernel<HD, NQT, KS, POLY, RS>, grid, dim3(kThreads), ACfg<HD, NQT, KS, RS>::SMEM_BYTES, stream, op.p,
-             op.map_q, op.map_k, op.map_v);
+  launch_pdl(attn_kernel<HD, NQT, KS, POLY, RS, PB>, grid, dim3(kThreads), ACfg<HD, NQT, KS, RS, PB>::SMEM_BYTES, stream,
+             op.p, op.map_q, op.map_k, op.map_v);
+}
+
+// CFGPP_ATTN_PBUF=2|1: double-buffered P (K / V ring of 2 instead of 3 to stay inside 227 KB) for head dim 64
+int attn_pbuf() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("CFGPP_ATTN_PBUF");
+    v = e ? atoi(e) : kDefaultPbuf;
+    if (v != 1 && v != 2) v = kDefaultPbuf;
+  }
+  return v;
 }
 
 // CFGPP_ATTN_ROWSUM_MMA=1|0: row sums from the tensor pipe (ones column appended to V) for head dim 64
@@ -439,6 +463,7 @@ void attn_configure() {
   configure_one<64, 2, 3, 4>();
   configure_one<64, 2, 3, 3>();
   configure_one<64, 2, 3, 0, true>();
+  configure_one<64, 2, 2, 0, false, 2>();
   configure_one<128, 1, 2>();
   configure_one<192, 1, 1>();
   xattn_configure();
@@ -467,6 +492,7 @@ void run_attn_op(const AttnOp& op, cudaStream_t stream) {
   attn_configure();
   switch (op.hd_pad) {
     case 64:
+      if (attn_pbuf() == 2) return launch<64, 2, 2, 0, false, 2>(op, stream);
       if (attn_rowsum_mma()) return launch<64, 2, 3, 0, true>(op, stream);
       switch (attn_poly()) {
         case 8: return launch<64, 2, 3, 8>(op, stream);
