@@ -211,15 +211,18 @@ def test_layernorm(M, Cc):
     gate(f'layernorm {M}x{Cc}', nv.op_layernorm(x, gamma, beta), ref, TOL_NORM)
 
 
-def test_attention_persistent_variant_in_subprocess():
-    """The opt-in persistent self-attention kernel (CFGPP_PATTN=1, attention_persist.cu) is kept validated: the
+@pytest.mark.parametrize("switch", ["CFGPP_PATTN=1", "CFGPP_ATTN_POLY=4", "CFGPP_ATTN_ROWSUM_MMA=1", "CFGPP_ATTN_PBUF=2"])
+def test_attention_opt_in_variants_in_subprocess(switch):
+    """The opt-in attention variants of round 2 — persistent kernel, polynomial exp2 on the FMA pipe, row sums on the
+    tensor pipe, double-buffered P: all measured no faster than the default, DESIGN.md §7 — stay validated: the
     attention parity tests re-run in a child process with the switch set (the dispatch reads it once per process)."""
     import os
     import subprocess
     import sys
-    if os.environ.get("CFGPP_PATTN") == "1":
+    if os.environ.get("CFGPP_ATTN_CHILD") == "1":
         pytest.skip("already inside the child")
-    env = dict(os.environ, CFGPP_PATTN="1")
+    k, v = switch.split("=")
+    env = dict(os.environ, CFGPP_ATTN_CHILD="1", **{k: v})
     r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-k",
                         "test_attention and not subprocess", "-x"], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
