@@ -882,8 +882,12 @@ void finish_op(GemmOp& op, const __half* w, int force_bn) {
     const double piece = static_cast<double>(rem) * p.num_k_blocks / max_clusters;
     const double saved = (p.num_k_blocks - piece) * op.bn / 160.0;
     const bool eligible = p.conv || streamk_linear();
-    // pieces at least half a tile deep: a tile then has at most three pieces, i.e. <= 2 partials to sum per chunk
-    if (eligible && saved >= streamk_min_saved() && piece >= 2.0 && piece >= streamk_min_piece() * p.num_k_blocks) {
+    // pieces at least half a tile deep: a tile then has at most three pieces, i.e. <= 2 partials to sum per chunk —
+    // unless the saving is large anyway: with fewer tiles than clusters and a long K (SD v1.5's 8 x 8 level: 16 tiles of
+    // 180 k-blocks on 74 clusters, 89 us at 242 TFLOP/s) every cluster takes ~1/5 of a tile and the fix-up sums 4-5
+    // partials per chunk, still a small price for a 4.6x shorter main loop
+    const bool deep_enough = piece >= streamk_min_piece() * p.num_k_blocks || saved >= 60.0;
+    if (eligible && saved >= streamk_min_saved() && piece >= 2.0 && deep_enough) {
       op.grid = op.cluster * max_clusters;  // all clusters take part, also when there are fewer tiles than clusters
       streamk_buffers(&p.sk_ws, &p.sk_flags);
     }

@@ -112,7 +112,9 @@ def test_conv3x3_streamk_repeatable():
     (2, 8, 8, 128, 128, True, False), (1, 128, 128, 320, 320, True, False), (4, 32, 32, 1280, 1280, False, True),
     # non-square / non-power-of-two H (landscape aspect buckets), W > 128 row segments (VAE decoder levels)
     (2, 96, 128, 64, 128, True, False), (1, 24, 32, 128, 128, False, True), (3, 6, 64, 64, 64, False, False),
-    (1, 40, 256, 64, 64, False, True), (1, 16, 1024, 64, 64, True, False)])
+    (1, 40, 256, 64, 64, False, True), (1, 16, 1024, 64, 64, True, False),
+    # fewer tiles than clusters with a long K: every tile is split over ~5 clusters (stream-K with 4-5 partials)
+    (8, 8, 8, 1280, 1280, True, False), (8, 8, 8, 2560, 1280, False, True)])
 def test_conv3x3(B, H, W, Cin, Cout, ht, hr):
     """Zero padding comes from TMA out-of-bounds fill; edge pixels are therefore the interesting ones."""
     from cfgpp_b200 import _native as nv

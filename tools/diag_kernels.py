@@ -434,20 +434,19 @@ def diag_unet(which=("tiny_sdxl", "tiny_sd15")):
         guarded(label, run)
 
 
-def prof_unet():
-    """Per-plan-entry CUDA-event profile of one eager SDXL forward (batch 2), aggregated by op type."""
+def prof_unet(name="sdxl", B=2, hw=128):
+    """Per-plan-entry CUDA-event profile of one eager forward (SDXL batch 2 by default), aggregated by op type."""
     import collections
     import re
     from cfgpp_b200 import config as C, weights as Wt
     from cfgpp_b200.engine import NativeUNet
-    cfg = C.sdxl_config()
-    B, hw = 2, 128
+    cfg = C.CONFIGS[name]()
     sd = Wt.synthetic_state_dict(cfg, seed=1234, device=dev)
     z, uc, c, add = _unet_inputs(cfg, B, hw)
     net = NativeUNet(cfg, sd, dev)
     del sd
     net.prepare(B, hw, hw)
-    net.set_prompt(torch.cat([uc, c]), add["text_embeds"], add["time_ids"].float())
+    net.set_prompt(torch.cat([uc, c]), add["text_embeds"] if add else None, add["time_ids"].float() if add else None)
     net.profile_forward(z, 500.0)
     prof = net.profile_forward(z, 500.0)
     agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
@@ -456,9 +455,10 @@ def prof_unet():
         m = re.match(r"(down_blocks|up_blocks)\.(\d)", name)
         if m:
             i = int(m.group(2))
-            lvl = f"L{i}" if m.group(1) == "down_blocks" else f"L{2 - i}"
+            top = len(cfg.block_out_channels) - 1
+            lvl = f"L{i}" if m.group(1) == "down_blocks" else f"L{top - i}"
         elif name.startswith("mid_block"):
-            lvl = "L2"
+            lvl = f"L{len(cfg.block_out_channels) - 1}"
         short = re.sub(r"^.*?(resnets|attentions|downsamplers|upsamplers)\.\d+\.", "", name)
         short = re.sub(r"transformer_blocks\.\d+\.", "", short)
         key = (lvl, short, kind)
@@ -559,5 +559,7 @@ if __name__ == "__main__":
         bench_unet()
     if "prof_unet" in which:
         prof_unet()
+    if "prof_unet_sd15" in which:
+        prof_unet("sd15", 4, 64)
     nbad = sum(1 for _, ok in RESULTS if not ok)
     print(f"=== {len(RESULTS) - nbad}/{len(RESULTS)} cases OK in {time.time() - t0:.1f}s ===", flush=True)
