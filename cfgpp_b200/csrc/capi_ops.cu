@@ -1,8 +1,6 @@
 // cfgpp_b200 — C ABI, operator-level entry points (one call = one kernel launch on the caller's stream).
 // Declared in include/cfgpp_b200.h. No C++ exception crosses the boundary: every entry point returns an int
 // status (0 = OK) and records a message retrievable with cfgpp_last_error().
-#include <cstdlib>
-
 #include "capi_util.h"
 #include "attention.cuh"
 #include "gemm.cuh"
@@ -10,21 +8,6 @@
 #include "../../include/cfgpp_b200.h"
 
 using namespace cfgpp;
-
-namespace {
-// At the operator level the "weight" is whatever tensor the caller passes — possibly the output of the kernel it just
-// launched on the same stream — so the early weight fetch of the GEMM (before griddepcontrol.wait) is off unless the
-// caller vouches for a static B operand (CFGPP_OP_STATIC_B=1: the micro-benchmarks). The UNet / VAE plans, whose B
-// operands are packed weights, always use it.
-int op_b_dynamic() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CFGPP_OP_STATIC_B");
-    v = (e && e[0] == '1') ? 0 : 1;
-  }
-  return v;
-}
-}  // namespace
 
 extern "C" {
 
@@ -35,7 +18,6 @@ CFGPP_API int cfgpp_op_linear(const void* a, int lda, const void* a2, int lda2, 
     GemmOp op = make_linear_op((const __half*)a, lda, (const __half*)a2, lda2, k_split, (const __half*)w, M, N, K,
                                (const __half*)bias, (const __half*)addend, ld_add, add_rows_per_group, (__half*)out,
                                ldc, geglu != 0, force_bn);
-    op.p.b_dynamic = op_b_dynamic();
     run_gemm_op(op, (cudaStream_t)stream);
   });
 }
@@ -51,7 +33,6 @@ CFGPP_API int cfgpp_dbg_linear_timeline(const void* a, int lda, const void* w, i
     CFGPP_CHECK_CUDA(cudaMalloc(&d, sizeof(unsigned long long) * 16 * op.grid));
     CFGPP_CHECK_CUDA(cudaMemset(d, 0, sizeof(unsigned long long) * 16 * op.grid));
     op.p.timeline = d;
-    op.p.b_dynamic = op_b_dynamic();
     for (int i = 0; i < iters; ++i) run_gemm_op(op, (cudaStream_t)stream);
     CFGPP_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     CFGPP_CHECK_CUDA(cudaMemcpy(host_out, d, sizeof(unsigned long long) * 16 * op.grid, cudaMemcpyDeviceToHost));
@@ -66,7 +47,6 @@ CFGPP_API int cfgpp_op_conv3x3(const void* x, int B, int H, int W, int Cin, cons
   return guarded([&] {
     GemmOp op = make_conv3x3_op((const __half*)x, B, H, W, Cin, (const __half*)w, Cout, (const __half*)bias,
                                 (const __half*)addend, ld_add, add_rows_per_group, (__half*)out, force_bn);
-    op.p.b_dynamic = op_b_dynamic();
     run_gemm_op(op, (cudaStream_t)stream);
   });
 }

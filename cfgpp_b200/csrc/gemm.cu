@@ -133,6 +133,8 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
   if (threadIdx.x == 0) TL(1);
   pdl_launch_dependents();  // the next kernel may start its prologue on SMs this grid leaves
+  pdl_wait();               // everything above overlapped the previous kernel's tail; its outputs are needed below
+  if (threadIdx.x == 0) TL(2);
 
   // tiles are enumerated as (m-group, n) with CL vertically adjacent M blocks per group; a cluster walks the groups,
   // CTA `cta_rank` takes M block  group * CL + cta_rank  (possibly a phantom block past M: loads zero-fill, stores clip)
@@ -225,40 +227,11 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
   // partial accumulator of (cluster c, CTA rank r): [BN / 32 column chunks][4 lane quarters][8][32 lanes] float4
   auto sk_ws = [&](int c) { return p.sk_ws + (static_cast<size_t>(c) * CL + cta_rank) * (static_cast<size_t>(BM) * BN); };
 
-  // The B operand of every UNet / VAE-conv launch is a WEIGHT tile: it does not depend on the previous kernel, and it
-  // comes from HBM (5 GB of weights stream through the 126 MB L2 every forward). The producer therefore issues the
-  // weight loads of its first ring stages BEFORE griddepcontrol.wait, i.e. under the previous kernel's tail; only the
-  // activation (A) loads of those stages wait for the dependency. (b_dynamic: the B operand is an activation — the
-  // VAE's Q K^T / P V products.)
-  int n_pre = 0;
-  if (warp_idx == kProducerWarp && !p.b_dynamic && n_items > 0) {
-    const Item it0 = item_at(0);
-    const int len0 = it0.kb1 - it0.kb0;
-    n_pre = len0 < C::STAGES ? len0 : C::STAGES;
-    const int n_blk0 = tile_n_blk(it0.tile);
-    if (elect_one()) {
-      for (int st = 0; st < n_pre; ++st) {
-        uint8_t* sb = smem + st * C::STAGE_BYTES + A_BYTES;
-        if constexpr (CL == 1) {
-          mbar_arrive_expect_tx(&full_bar[st], C::STAGE_BYTES);
-          tma_load_2d(sb, &map_b, &full_bar[st], (it0.kb0 + st) * BK, n_blk0 * BN);
-        } else {
-          if (is_leader_cta) mbar_arrive_expect_tx(&full_bar[st], 2 * C::STAGE_BYTES);
-          tma_load_2d_cg2(sb, &map_b, &full_bar[st], (it0.kb0 + st) * BK, n_blk0 * BN + cta_rank * (BN / 2));
-        }
-      }
-    }
-    __syncwarp();
-  }
-  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are needed below
-  if (threadIdx.x == 0) TL(2);
-
   if (warp_idx == kProducerWarp) {
     {
       // ===================== TMA producer (whole warp walks the loop, one elected lane issues) ============
       int stage = 0;
       uint32_t phase = 0;
-      int pre_left = n_pre;  // stages of the first item whose weight tile (and expect_tx) are already in flight
       for (int item_i = 0; item_i < n_items; ++item_i) {
         const Item item = item_at(item_i);
         const int tile = item.tile;
@@ -281,7 +254,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
             // non-elected lanes only keep the loop state in step
           } else if constexpr (CL == 1) {
             if (item_i == 0 && kb == item.kb0) TL(3);
-            if (pre_left == 0) mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+            mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
             if (p.conv) {
               const int tap = kb / p.cpb;
               const int cb = kb - tap * p.cpb;
@@ -294,11 +267,11 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
               else
                 tma_load_2d(sa, &map_a2, &full_bar[stage], k0 - p.k_split, m0);
             }
-            if (pre_left == 0) tma_load_2d(sb, &map_b, &full_bar[stage], kb * BK, n_blk * BN);
+            tma_load_2d(sb, &map_b, &full_bar[stage], kb * BK, n_blk * BN);
           } else {
             if (item_i == 0 && kb == item.kb0) TL(3);
             // both CTAs fill their own smem; all bytes are accounted on the leader's barrier (the MMA issuer's)
-            if (is_leader_cta && pre_left == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+            if (is_leader_cta) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
             if (p.conv) {
               const int tap = kb / p.cpb;
               const int cb = kb - tap * p.cpb;
@@ -311,10 +284,8 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
               else
                 tma_load_2d_cg2(sa, &map_a2, &full_bar[stage], k0 - p.k_split, m0);
             }
-            if (pre_left == 0)
-              tma_load_2d_cg2(sb, &map_b, &full_bar[stage], kb * BK, n_blk * BN + cta_rank * (BN / 2));
+            tma_load_2d_cg2(sb, &map_b, &full_bar[stage], kb * BK, n_blk * BN + cta_rank * (BN / 2));
           }
-          if (pre_left > 0) --pre_left;
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -984,14 +955,7 @@ GemmOp make_conv3x3_op(const __half* x, int B, int H, int W, int Cin, const __ha
   return op;
 }
 
-void run_gemm_op(const GemmOp& op_in, cudaStream_t stream) {
-  // CFGPP_NO_WPREFETCH=1: A/B switch for the early weight fetch (treat every B operand as dynamic)
-  static const bool no_prefetch = [] {
-    const char* e = getenv("CFGPP_NO_WPREFETCH");
-    return e != nullptr && e[0] == '1';
-  }();
-  GemmOp op = op_in;
-  if (no_prefetch) op.p.b_dynamic = 1;
+void run_gemm_op(const GemmOp& op, cudaStream_t stream) {
   CFGPP_REQUIRE(!(op.p.stats_in && (op.p.addend || op.p.stats_out)),
                 "a LayerNorm-fold consumer GEMM takes no addend and emits no row statistics");
   CFGPP_REQUIRE(!(op.p.geglu && (op.p.addend || op.p.stats_out)), "the GEGLU epilogue takes no addend / statistics");

@@ -46,7 +46,6 @@ struct GemmParams {
   float ln_inv_c, ln_eps;
   const float* ln_s;       // [N] fp32
   const float* ln_t;       // [N] fp32
-  int b_dynamic;           // 1: the B operand is an activation written by the previous kernel (no early weight fetch)
   // ---- stream-K for the remainder tiles (see gemm.cu "work schedule"); null = plain data-parallel tile walk ------
   float* sk_ws;            // per (cluster, CTA rank) partial accumulator, 128 x BN fp32 in the epilogue's lane order
   unsigned* sk_flags;      // [2 * 256] zero-initialised, self-resetting arrival / consumer counters

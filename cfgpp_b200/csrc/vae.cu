@@ -134,18 +134,12 @@ __half* VaeDecoder::build_attention(const std::string& prefix, const __half* x, 
     const __half* ns = normp + static_cast<size_t>(s) * N * C;
     __half* os = o + static_cast<size_t>(s) * N * C;
     // S = Q K^T                                   [N x N]
-    GemmOp op_s = make_linear_op(qs, C, nullptr, 0, 0, ks, N, N, C, nullptr, nullptr, 0, 1, sc, N, false);
-    op_s.p.b_dynamic = 1;  // B = K: an activation, not a weight
-    add_gemm(op_s);
+    add_gemm(make_linear_op(qs, C, nullptr, 0, 0, ks, N, N, C, nullptr, nullptr, 0, 1, sc, N, false));
     add([=](cudaStream_t st) { run_vae_row_softmax(sc, N, N, scale_log2e, st); });
     // V0^T = Wv X^T (no bias)                      [C x N]: the MN-major operand the P V GEMM needs as its "weight"
-    GemmOp op_vt = make_linear_op(wv, C, nullptr, 0, 0, ns, C, N, C, nullptr, nullptr, 0, 1, vt, N, false);
-    op_vt.p.b_dynamic = 1;  // B = the normalised tokens
-    add_gemm(op_vt);
+    add_gemm(make_linear_op(wv, C, nullptr, 0, 0, ns, C, N, C, nullptr, nullptr, 0, 1, vt, N, false));
     // O = P V0 + b_v (rows of P sum to 1, so the value bias commutes with the softmax average)   [N x C]
-    GemmOp op_pv = make_linear_op(sc, N, nullptr, 0, 0, vt, N, C, N, bv, nullptr, 0, 1, os, C, false);
-    op_pv.p.b_dynamic = 1;  // B = V0^T
-    add_gemm(op_pv);
+    add_gemm(make_linear_op(sc, N, nullptr, 0, 0, vt, N, C, N, bv, nullptr, 0, 1, os, C, false));
   }
   __half* out = next_out();
   add_gemm(make_linear_op(o, C, nullptr, 0, 0, plain(prefix + ".to_out.0.weight"), NB * N, C, C,
