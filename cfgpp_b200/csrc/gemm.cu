@@ -801,19 +801,25 @@ double streamk_min_piece() {  // smallest piece as a fraction of a tile's k-bloc
   }
   return v;
 }
-// One workspace per device: partial accumulators for up to 148 CTAs ([128 x 256] fp32 each) + the flag words.
+// Stream-K workspace: partial accumulators for up to 148 CTAs ([128 x 256] fp32 each) + the flag words. Launches that
+// share a workspace must be stream-ordered (the flags are per cluster id), so every model handle owns one
+// (StreamKScope around its plan building; a handle runs on one stream at a time) and the operator-level entry points
+// fall back to one buffer per device.
+thread_local float* t_sk_ws = nullptr;
+thread_local unsigned* t_sk_flags = nullptr;
+
 void streamk_buffers(float** ws, unsigned** flags) {
+  if (t_sk_ws != nullptr) {  // a model handle is building its plan: its own workspace
+    *ws = t_sk_ws;
+    *flags = t_sk_flags;
+    return;
+  }
   static float* g_ws[16] = {nullptr};
   static unsigned* g_flags[16] = {nullptr};
   int dev = 0;
   CFGPP_CHECK_CUDA(cudaGetDevice(&dev));
   CFGPP_REQUIRE(dev >= 0 && dev < 16, "device index out of range");
-  if (g_ws[dev] == nullptr) {
-    CFGPP_CHECK_CUDA(cudaMalloc(&g_ws[dev], static_cast<size_t>(kSkMaxClusters) * BM * 256 * sizeof(float)));
-    CFGPP_CHECK_CUDA(cudaMalloc(&g_flags[dev], 2 * kSkMaxClusters * sizeof(unsigned)));
-    CFGPP_CHECK_CUDA(cudaMemset(g_flags[dev], 0, 2 * kSkMaxClusters * sizeof(unsigned)));
-    CFGPP_CHECK_CUDA(cudaDeviceSynchronize());
-  }
+  if (g_ws[dev] == nullptr) streamk_alloc(&g_ws[dev], &g_flags[dev]);
   *ws = g_ws[dev];
   *flags = g_flags[dev];
 }
@@ -895,6 +901,25 @@ void finish_op(GemmOp& op, const __half* w, int force_bn) {
 }
 
 }  // namespace
+
+void streamk_alloc(float** ws, unsigned** flags) {
+  CFGPP_CHECK_CUDA(cudaMalloc(ws, static_cast<size_t>(kSkMaxClusters) * BM * 256 * sizeof(float)));
+  CFGPP_CHECK_CUDA(cudaMalloc(flags, 2 * kSkMaxClusters * sizeof(unsigned)));
+  CFGPP_CHECK_CUDA(cudaMemset(*flags, 0, 2 * kSkMaxClusters * sizeof(unsigned)));
+  CFGPP_CHECK_CUDA(cudaDeviceSynchronize());
+}
+void streamk_free(float* ws, unsigned* flags) {
+  if (ws) cudaFree(ws);
+  if (flags) cudaFree(flags);
+}
+StreamKScope::StreamKScope(float* ws, unsigned* flags) : prev_ws_(t_sk_ws), prev_flags_(t_sk_flags) {
+  t_sk_ws = ws;
+  t_sk_flags = flags;
+}
+StreamKScope::~StreamKScope() {
+  t_sk_ws = prev_ws_;
+  t_sk_flags = prev_flags_;
+}
 
 // opt every instantiation into its dynamic shared memory size once per process (not capturable: done eagerly)
 void gemm_configure() {

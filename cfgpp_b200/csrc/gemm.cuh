@@ -73,6 +73,22 @@ GemmOp make_conv3x3_op(const __half* x, int B, int H, int W, int Cin, const __ha
 
 void run_gemm_op(const GemmOp& op, cudaStream_t stream);
 
+// Stream-K workspace ownership (see gemm.cu): a model handle allocates its own buffers and wraps its plan building in a
+// StreamKScope, so ops of different handles — which may run on different streams — never share flags.
+void streamk_alloc(float** ws, unsigned** flags);
+void streamk_free(float* ws, unsigned* flags);
+class StreamKScope {
+ public:
+  StreamKScope(float* ws, unsigned* flags);
+  ~StreamKScope();
+  StreamKScope(const StreamKScope&) = delete;
+  StreamKScope& operator=(const StreamKScope&) = delete;
+
+ private:
+  float* prev_ws_;
+  unsigned* prev_flags_;
+};
+
 // Geometry the implicit-GEMM A tile (a 4-D TMA box of 128 consecutive output pixels) can address:
 //   W > 128           : W % 128 == 0 (a tile = a 128-pixel row segment), any H;
 //   W <= 128, pow2    : a tile = 128 / W whole rows: H must be a multiple of that (e.g. 96 x 128, 48 x 64, 24 x 32 —

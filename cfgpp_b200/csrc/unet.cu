@@ -127,6 +127,7 @@ Unet::Unet(const cfgpp_model_desc& d, int device) : d_(d), device_(device) {
   has_aug_ = d.addition_time_embed_dim > 0;
   gemm_configure();
   attn_configure();
+  streamk_alloc(&sk_ws_, &sk_flags_);
   CFGPP_CHECK_CUDA(cudaStreamCreateWithFlags(&capture_stream_, cudaStreamNonBlocking));
   CFGPP_CHECK_CUDA(cudaStreamCreateWithFlags(&capture_stream2_, cudaStreamNonBlocking));
   CFGPP_CHECK_CUDA(cudaEventCreateWithFlags(&fork_ev_, cudaEventDisableTiming));
@@ -143,6 +144,7 @@ Unet::~Unet() {
   for (auto& kv : raw_) cudaFree(kv.second.p);
   for (void* p : weight_allocs_) cudaFree(p);
   for (void* p : act_allocs_) cudaFree(p);
+  streamk_free(sk_ws_, sk_flags_);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -645,6 +647,7 @@ void Unet::prepare(int batch, int h_lat, int w_lat) {
   }
   CFGPP_CHECK_CUDA(cudaSetDevice(device_));
   CFGPP_CHECK_CUDA(cudaDeviceSynchronize());
+  StreamKScope sk_scope(sk_ws_, sk_flags_);  // every GEMM op built below parks its stream-K partials in OUR workspace
   // from here on the old plan is gone: a throw below must not leave the handle looking prepared
   prepared_ = false;
   nsteps_ = 0;

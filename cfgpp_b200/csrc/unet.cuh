@@ -174,6 +174,8 @@ class Unet {
   __half* conv_in_out_ = nullptr;
   __half *conv_in_w_ = nullptr, *conv_in_b_ = nullptr, *conv_out_w_ = nullptr, *conv_out_b_ = nullptr;
 
+  float* sk_ws_ = nullptr;       // this handle's stream-K workspace (gemm.cuh StreamKScope)
+  unsigned* sk_flags_ = nullptr;
   cudaGraph_t graph_ = nullptr;
   cudaGraphExec_t graph_exec_ = nullptr;
   bool graph_valid_ = false;

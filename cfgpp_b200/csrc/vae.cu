@@ -17,12 +17,14 @@ VaeDecoder::VaeDecoder(const cfgpp_vae_desc& d, int device) : d_(d), device_(dev
     CFGPP_REQUIRE(d.block_out_channels[i] % 64 == 0, "decoder channel counts must be multiples of 64");
   CFGPP_REQUIRE(d.scaling_factor > 0.f, "scaling_factor must be positive");
   gemm_configure();
+  streamk_alloc(&sk_ws_, &sk_flags_);
 }
 
 VaeDecoder::~VaeDecoder() {
   for (auto& kv : raw_) cudaFree(kv.second.p);
   for (void* p : weight_allocs_) cudaFree(p);
   for (void* p : act_allocs_) cudaFree(p);
+  streamk_free(sk_ws_, sk_flags_);
 }
 
 void VaeDecoder::load_weight(const std::string& key, const void* data, const int64_t* shape, int ndim, int dtype,
@@ -157,6 +159,7 @@ void VaeDecoder::prepare(int batch, int h_lat, int w_lat) {
                   "conv3x3 tiler: unsupported decoder level geometry " + std::to_string(h) + "x" + std::to_string(w));
   CFGPP_CHECK_CUDA(cudaSetDevice(device_));
   CFGPP_CHECK_CUDA(cudaDeviceSynchronize());
+  StreamKScope sk_scope(sk_ws_, sk_flags_);  // the decoder's GEMM ops use its own stream-K workspace
   for (void* p : act_allocs_) cudaFree(p);
   act_allocs_.clear();
   plan_.clear();

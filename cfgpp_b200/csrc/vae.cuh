@@ -87,6 +87,8 @@ class VaeDecoder {
   __half *s_norm_ = nullptr, *s_h1_ = nullptr, *s_sc_ = nullptr, *s_up_ = nullptr, *zq_ = nullptr;
   __half *s_q_ = nullptr, *s_k_ = nullptr, *s_vt_ = nullptr, *s_scores_ = nullptr, *s_o_ = nullptr;
   float* gn_partial_ = nullptr;
+  float* sk_ws_ = nullptr;  // this handle's stream-K workspace (gemm.cuh StreamKScope)
+  unsigned* sk_flags_ = nullptr;
 };
 
 }  // namespace cfgpp
