@@ -89,6 +89,17 @@ def op_conv3x3(x_nhwc: torch.Tensor, w_packed: torch.Tensor, bias=None, addend=N
     return out
 
 
+def op_conv3x3_s2(x_nhwc: torch.Tensor, w_packed: torch.Tensor, bias=None) -> torch.Tensor:
+    """Downsample2D conv: x [B,H,W,Cin] fp16 NHWC (even H, W), w_packed [Cout, 9*Cin] (tap-major) -> [B,H/2,W/2,Cout]."""
+    lib = load()
+    B, H, W, Cin = x_nhwc.shape
+    Cout = w_packed.shape[0]
+    out = torch.empty((B, H // 2, W // 2, Cout), dtype=torch.float16, device=x_nhwc.device)
+    check(lib.cfgpp_op_conv3x3_s2(ptr(x_nhwc), c_int(B), c_int(H), c_int(W), c_int(Cin), ptr(w_packed), c_int(Cout),
+                                  ptr(bias), ptr(out), stream_ptr()))
+    return out
+
+
 def op_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, head_dim: int = 64) -> torch.Tensor:
     """q [B,Nq,H*P], k/v [B,Nkv,H*P] fp16 (views with a row stride are fine) -> [B,Nq,H*P]; P = head_dim rounded up
     to a multiple of 64, the padding columns of every head being zero."""

@@ -25,7 +25,8 @@ struct GemmParams {
   int num_m_blocks, num_n_blocks, num_k_blocks;
   int conv;     // 0 linear, 1 conv3x3
   int cpb;      // conv: channel blocks (Cin / 64) per tap
-  int H, W;     // conv: spatial size
+  int H, W;     // conv: OUTPUT spatial size
+  int conv_stride;  // conv: 1, or 2 (Downsample2D: the A tile is fetched through a tensor map with element strides 2)
   int k_split;  // linear: first K index served by the second A map (== K when single-source)
   const __half* bias;
   const __half* addend;
@@ -67,9 +68,10 @@ GemmOp make_linear_op(const __half* a, int lda, const __half* a2, int lda2, int 
                       __half* out, int ldc, bool geglu, int force_bn = 0);
 
 // Conv3x3 stride 1 pad 1 on NHWC input x [B,H,W,Cin], weight [Cout][9][Cin], out NHWC [B,H,W,Cout].
+// stride 2 (pad 1): x is [B,H,W,Cin] with even H, W; out is [B,H/2,W/2,Cout].
 GemmOp make_conv3x3_op(const __half* x, int B, int H, int W, int Cin, const __half* w, int Cout,
                        const __half* bias, const __half* addend, int ld_add, int add_rows_per_group, __half* out,
-                       int force_bn = 0);
+                       int force_bn = 0, int stride = 1);
 
 void run_gemm_op(const GemmOp& op, cudaStream_t stream);
 

@@ -43,7 +43,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 CUtensorMap make_tmap_f16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                          const uint32_t* box, int swizzle_bytes) {
+                          const uint32_t* box, int swizzle_bytes, const uint32_t* elem_strides) {
   CUtensorMap m;
   cuuint64_t gdim[5];
   cuuint64_t gstr[4];
@@ -52,7 +52,7 @@ CUtensorMap make_tmap_f16(const void* base, int rank, const uint64_t* dims, cons
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
-    estr[i] = 1;
+    estr[i] = elem_strides ? elem_strides[i] : 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   CFGPP_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16B aligned");

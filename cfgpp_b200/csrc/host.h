@@ -71,8 +71,10 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 
 // Generic fp16 tiled tensor map, 128B swizzle. dims/strides innermost first; strides[i] is the byte
 // stride of dim i+1 (dim 0 is contiguous). OOB elements are zero-filled by the hardware.
+// `elem_strides` (optional, per dim): traversal stride — with stride s a box extent b loads ceil(b / s) elements
+// (every s-th one from the box origin); used by the stride-2 convolution.
 CUtensorMap make_tmap_f16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                          const uint32_t* box, int swizzle_bytes = 128);
+                          const uint32_t* box, int swizzle_bytes = 128, const uint32_t* elem_strides = nullptr);
 
 // 2D row-major [rows][cols] fp16 with leading dimension ld (elements); box = (64 cols, box_rows).
 CUtensorMap make_tmap_2d(const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);

@@ -597,12 +597,22 @@ Unet::Act Unet::build_downsample(const std::string& prefix, Act x, int H, int W)
   const int C = x.C;
   const int Ho = H / 2, Wo = W / 2;
   const size_t Mo = static_cast<size_t>(bnb_) * Ho * Wo;
-  Scratch* s_col = scratch(btag_ + "im2col", Mo * 9 * C);
+  static const bool use_im2col = [] {  // CFGPP_NO_S2TMA=1: the round-1 path (materialised stride-2 im2col + plain GEMM)
+    const char* e = getenv("CFGPP_NO_S2TMA");
+    return e != nullptr && e[0] == '1';
+  }();
+  Scratch* s_col = use_im2col ? scratch(btag_ + "im2col", Mo * 9 * C) : nullptr;
   __half* out = g_dry ? nullptr : alloc_act(Mo * C);
   if (g_dry) {
     raw(prefix + ".conv.weight"); raw(prefix + ".conv.bias");
     workspace_bytes_ += Mo * C * sizeof(__half);
     return Act{nullptr, C};
+  }
+  if (!use_im2col) {
+    // stride-2 conv as an implicit GEMM: the A tile of every tap comes through a tensor map with element strides 2
+    add_gemm(prefix + ".conv", make_conv3x3_op(x.p, bnb_, H, W, C, packed_conv3x3(prefix + ".conv.weight"), C,
+                                               plain(prefix + ".conv.bias"), nullptr, 0, 1, out, 0, 2));
+    return Act{out, C};
   }
   const int NB = bnb_;
   const __half* xp = x.p;

@@ -170,6 +170,10 @@ int cfgpp_op_linear(const void* a, int lda, const void* a2, int lda2, int k_spli
                     int geglu, int force_bn, void* stream);
 int cfgpp_op_conv3x3(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias,
                      const void* addend, int ld_add, int add_rows_per_group, void* out, int force_bn, void* stream);
+/* Downsample2D: 3x3, stride 2, pad 1 on NHWC x [B,H,W,Cin] (even H, W) -> [B,H/2,W/2,Cout]; the A tile is fetched by TMA
+ * with element strides 2 (no im2col copy). */
+int cfgpp_op_conv3x3_s2(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias, void* out,
+                        void* stream);
 /* head h of q / k / v / out occupies columns [h*P, h*P + head_dim) with P = head_dim rounded up to a multiple of 64
  * (columns head_dim..P-1 must be zero in q / k / v and come back zero in out). */
 int cfgpp_op_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B,

@@ -96,6 +96,20 @@ def test_linear_dual_source_and_geglu():
     gate('geglu', out, ref, TOL_GEMM)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(4, 128, 128, 320, 320), (4, 64, 64, 640, 640), (2, 32, 32, 128, 128),
+                                            (1, 16, 16, 64, 64), (2, 96, 128, 64, 64)])
+def test_conv3x3_stride2(B, H, W, Cin, Cout):
+    """Downsample2D (3x3, stride 2, pad 1): the A tiles come through a tensor map with element strides 2 — the first
+    row / column of taps starts at input coordinate -1 (TMA zero fill), every second pixel is fetched."""
+    from cfgpp_b200 import _native as nv
+    g = torch.Generator().manual_seed(H + Cin)
+    x, w, bias = rnd(g, B, Cin, H, W), rnd(g, Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5), rnd(g, Cout)
+    out = nv.op_conv3x3_s2(x.permute(0, 2, 3, 1).contiguous(), w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous(),
+                           bias).reshape(-1, Cout)
+    ref = torch.nn.functional.conv2d(x.float(), w.float(), bias.float(), stride=2, padding=1).half()
+    gate(f'conv3x3 stride 2 {B}x{H}x{W} {Cin}->{Cout}', out, ref.permute(0, 2, 3, 1).reshape(-1, Cout), TOL_GEMM)
+
+
 def test_conv3x3_streamk_repeatable():
     """The conv shapes of the 1280-channel level take the stream-K split by default: 10 launches, bit-identical."""
     from cfgpp_b200 import _native as nv
