@@ -21,6 +21,7 @@ import torch
 from . import kdiffusion as K
 from . import schedule as S
 from .conditioning import SyntheticTextEncoder
+from .text_encoder import CLIPTextConfig, get_conditioner
 from .config import UNetConfig, sd15_config
 from .latent_sdxl import _Scheduler, get_engine
 
@@ -45,6 +46,18 @@ def get_solver(name: str, **kwargs):
 ########################
 
 
+def default_text_encoder(cfg: UNetConfig, device):
+    """CLIP-L (hidden 768) for SD v1.5; a proportionally narrow tower for the test-sized configs."""
+    d = cfg.cross_attention_dim
+    if d == 768:
+        return get_conditioner("clip_l", device, "sd15")
+    if d % 64:
+        return SyntheticTextEncoder(d, 0)
+    small = CLIPTextConfig(name=f"clip_{d}", vocab_size=1024, hidden_size=d, intermediate_size=4 * d, num_hidden_layers=2,
+                           num_attention_heads=d // 64, pad_token_id=1023)
+    return get_conditioner("", device, "sd15", cfg=small)
+
+
 class StableDiffusion(K.KDiffusionMixin):
     def __init__(self,
                  solver_config,
@@ -55,7 +68,9 @@ class StableDiffusion(K.KDiffusionMixin):
         self.dtype = kwargs.get("pipe_dtype", torch.float16)
         self.cfg: UNetConfig = kwargs.get("unet_config") or sd15_config()
         self.unet = get_engine(model_key, self.cfg, device, kwargs.get("state_dict"))
-        self.text_encoder = kwargs.get("text_encoder") or SyntheticTextEncoder(self.cfg.cross_attention_dim, 0)
+        # CLIP-L text tower on the native backend (text_encoder.py; the reference takes pipe.text_encoder,
+        # latent_diffusion.py:65-66). Pass `text_encoder=fn`, prompt -> (hidden (1,77,D), None), to override.
+        self.text_encoder = kwargs.get("text_encoder") or default_text_encoder(self.cfg, device)
         self.vae = kwargs.get("vae")
         if self.vae is None:
             # AutoencoderKL decoder on the native backend (vae.py; the reference uses pipe.vae, latent_diffusion.py:64)

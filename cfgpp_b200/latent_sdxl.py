@@ -25,6 +25,7 @@ import torch
 from . import kdiffusion as K
 from . import schedule as S
 from .conditioning import SyntheticTextEncoder
+from .text_encoder import CLIPTextConfig, ClipConditioner, get_conditioner
 from .config import UNetConfig, sdxl_config
 from .engine import NativeUNet
 from .weights import load_safetensors_state_dict, synthetic_state_dict
@@ -102,6 +103,27 @@ class _Scheduler:
         self.final_alpha_cumprod = sch.final_alpha_cumprod
 
 
+def default_text_encoders(cfg: UNetConfig, device):
+    """(text_enc_1, text_enc_2) for a UNet config: CLIP-L + OpenCLIP bigG for the real SDXL widths (768 + 1280 = 2048,
+    pooled 1280), proportionally narrow towers for the test-sized configs; widths that are not multiples of the 64-wide
+    CLIP head fall back to the shape-only stand-in of conditioning.py."""
+    d2 = cfg.pooled_dim
+    d1 = cfg.cross_attention_dim - d2
+    if d1 <= 0:
+        d1 = cfg.cross_attention_dim // 2
+        d2 = cfg.cross_attention_dim - d1
+    if (d1, d2, cfg.pooled_dim) == (768, 1280, 1280):
+        return (get_conditioner("clip_l", device, "sdxl"), get_conditioner("clip_bigg", device, "sdxl"))
+    if d1 % 64 or d2 % 64 or cfg.pooled_dim % 8:
+        return (SyntheticTextEncoder(d1, 0), SyntheticTextEncoder(d2, cfg.pooled_dim))
+
+    def small(name, d, proj, act, pad):
+        return CLIPTextConfig(name=name, vocab_size=1024, hidden_size=d, intermediate_size=4 * d, num_hidden_layers=2,
+                              num_attention_heads=d // 64, hidden_act=act, projection_dim=proj, pad_token_id=pad)
+    return (get_conditioner("", device, "sdxl", cfg=small(f"clip_{d1}", d1, 0, "quick_gelu", 1023)),
+            get_conditioner("", device, "sdxl", cfg=small(f"clip_{d2}_proj", d2, cfg.pooled_dim, "gelu", 0)))
+
+
 class SDXL(K.KDiffusionMixin):
     schedule_kind = "ddim"
     quantize = True
@@ -120,11 +142,9 @@ class SDXL(K.KDiffusionMixin):
         self.cfg = unet_config or sdxl_config()
         self.unet = get_engine(model_key, self.cfg, device, state_dict)
 
-        d1 = self.cfg.cross_attention_dim - self.cfg.pooled_dim
-        self.text_enc_1, self.text_enc_2 = text_encoders or (
-            SyntheticTextEncoder(d1 if d1 > 0 else self.cfg.cross_attention_dim // 2, 0),
-            SyntheticTextEncoder(self.cfg.cross_attention_dim - (d1 if d1 > 0 else self.cfg.cross_attention_dim // 2),
-                                 self.cfg.pooled_dim))
+        # CLIP text towers on the native backend (text_encoder.py; the reference takes pipe.text_encoder /
+        # pipe.text_encoder_2, latent_sdxl.py:46-49). Pass `text_encoders=(fn1, fn2)`, prompt -> (hidden, pooled), to override.
+        self.text_enc_1, self.text_enc_2 = text_encoders or default_text_encoders(self.cfg, device)
         if vae is None:
             # AutoencoderKL decoder on the native backend (vae.py; the reference loads madebyollin/sdxl-vae-fp16-fix,
             # latent_sdxl.py:44). Pass `vae=` (any object with decode(zt) / encode(x, dtype)) to override.
@@ -153,6 +173,8 @@ class SDXL(K.KDiffusionMixin):
     @torch.no_grad()
     def _text_embed(self, prompt, text_enc, clip_skip):
         prompt = prompt[0] if isinstance(prompt, (list, tuple)) else prompt
+        if isinstance(text_enc, ClipConditioner):
+            return text_enc(prompt, self.device, clip_skip=clip_skip)
         return text_enc(prompt, self.device)
 
     @torch.no_grad()

@@ -164,6 +164,37 @@ int cfgpp_vae_decode(cfgpp_vae_handle* h, const void* zt_dev, int z_dtype, int b
 /* Algorithmic FLOPs of one decode of the prepared shape, and its activation workspace. */
 int cfgpp_vae_stats(cfgpp_vae_handle* h, double* flops, size_t* workspace_bytes);
 
+/* ---- CLIP text encoder: replaces `self.text_encoder(ids)[0]` of latent_diffusion.py:93-115 and
+ * `text_enc(ids, output_hidden_states=True)` -> `hidden_states[-2]` / `[-(clip_skip + 2)]` / `[0]` of
+ * latent_sdxl.py:77-93 (transformers CLIPTextModel: openai/clip-vit-large-patch14; CLIPTextModelWithProjection:
+ * OpenCLIP ViT-bigG). Weights under the transformers keys (`text_model.*`, `text_projection.weight`). Tokenisation
+ * stays on the host (cfgpp_b200/tokenizer.py). ----- */
+typedef struct cfgpp_clip_desc {
+  int vocab_size;        /* 49408 */
+  int max_positions;     /* 77 */
+  int hidden_size;       /* 768 (CLIP-L) / 1280 (bigG); heads are 64 wide */
+  int intermediate_size; /* 3072 / 5120 */
+  int num_layers;        /* 12 / 32 */
+  int num_heads;         /* 12 / 20 */
+  int hidden_act;        /* 0 = quick_gelu (CLIP-L), 1 = gelu (bigG) */
+  int projection_dim;    /* 0 = CLIPTextModel; > 0 = CLIPTextModelWithProjection (1280) */
+  float layer_norm_eps;  /* 1e-5 */
+} cfgpp_clip_desc;
+typedef struct cfgpp_clip_handle cfgpp_clip_handle;
+int cfgpp_clip_create(const cfgpp_clip_desc* desc, int device, cfgpp_clip_handle** out);
+int cfgpp_clip_destroy(cfgpp_clip_handle* h);
+int cfgpp_clip_load_weight(cfgpp_clip_handle* h, const char* transformers_key, const void* data_dev, const int64_t* shape,
+                           int ndim, int dtype, void* stream);
+int cfgpp_clip_finalize_weights(cfgpp_clip_handle* h, void* stream);
+/* input_ids_dev: (batch, n_tokens) int32 token ids; pooled_index_dev: (batch) int32 row of the pooled token (the
+ * <|endoftext|> position the model's eos rule selects; may be null when pooled_out is null). Outputs, fp16, each may
+ * be null: hidden_out (batch, n_tokens, hidden) = hidden_states[num_layers - skip] (skip = 1: the penultimate layer SDXL
+ * conditions on; skip = clip_skip + 1 in general); last_hidden_out = final_layer_norm(hidden_states[-1]) (what SD v1.5
+ * conditions on); pooled_out (batch, projection_dim or hidden) = text_embeds / pooler_output. */
+int cfgpp_clip_encode(cfgpp_clip_handle* h, const int32_t* input_ids_dev, const int32_t* pooled_index_dev, int batch,
+                      int n_tokens, int skip, void* hidden_out, void* last_hidden_out, void* pooled_out, void* stream);
+int cfgpp_clip_stats(cfgpp_clip_handle* h, double* flops, size_t* workspace_bytes);
+
 /* ---- operator-level entry points (one kernel each; used by the kernel parity tests and micro-benchmarks) ----- */
 int cfgpp_op_linear(const void* a, int lda, const void* a2, int lda2, int k_split, const void* w, int M, int N, int K,
                     const void* bias, const void* addend, int ld_add, int add_rows_per_group, void* out, int ldc,

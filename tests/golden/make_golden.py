@@ -107,8 +107,54 @@ def vae_case(seed=4242, hw=16):
     return {"seed": seed, "hw": hw, "zt": zt, "image": OV.decode(m, zt).half()}
 
 
+def clip_ids(cfg, batch=3, seed=5):
+    """Well-formed prompts: <bos> body <eos> pad..., one of them filling all 77 positions."""
+    g = torch.Generator().manual_seed(seed)
+    T, bos, eos = cfg.max_position_embeddings, cfg.vocab_size - 2, cfg.vocab_size - 1
+    ids = torch.full((batch, T), cfg.pad_token_id, dtype=torch.int64)
+    for b, n in enumerate([7, 30, T - 2][:batch]):
+        ids[b, 0] = bos
+        ids[b, 1:1 + n] = torch.randint(1, cfg.vocab_size - 3, (n,), generator=g)
+        ids[b, 1 + n] = eos
+    return ids
+
+
+def clip_case(seed=777):
+    """Outputs of the REAL transformers CLIPTextModel / CLIPTextModelWithProjection (the classes the reference's
+    pipeline instantiates) on seeded tiny towers (tests/golden/r02_clip_golden.pt). The weights are regenerated from
+    the seed by text_encoder.synthetic_clip_state_dict, so only ids and outputs are stored."""
+    import transformers
+    from transformers import CLIPTextConfig, CLIPTextModel, CLIPTextModelWithProjection
+    from cfgpp_b200 import text_encoder as TE
+    out = {"transformers": transformers.__version__, "seed": seed, "cases": {}}
+    for name, proj, act in (("plain_quick_gelu", 0, "quick_gelu"), ("proj_gelu", 64, "gelu")):
+        cfg = TE.tiny_clip_config(proj, act)
+        sd = TE.synthetic_clip_state_dict(cfg, seed=seed, device="cpu")
+        hc = CLIPTextConfig(vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
+                            num_hidden_layers=cfg.num_hidden_layers, num_attention_heads=cfg.num_attention_heads,
+                            max_position_embeddings=cfg.max_position_embeddings, hidden_act=cfg.hidden_act,
+                            projection_dim=proj or 8, layer_norm_eps=cfg.layer_norm_eps, eos_token_id=cfg.eos_token_id,
+                            bos_token_id=cfg.vocab_size - 2, pad_token_id=cfg.pad_token_id)
+        m = (CLIPTextModelWithProjection if proj else CLIPTextModel)(hc).eval()
+        missing, unexpected = m.load_state_dict({k: v.float() for k, v in sd.items()}, strict=False)
+        assert not unexpected and all(k.endswith("position_ids") for k in missing), (missing, unexpected)
+        ids = clip_ids(cfg)
+        with torch.no_grad():
+            o = m(ids, output_hidden_states=True)
+        out["cases"][name] = {"proj": proj, "act": act, "ids": ids.to(torch.int32),
+                              "hidden_states": [h.half() for h in o.hidden_states],
+                              "last_hidden_state": o.last_hidden_state.half(),
+                              "pooled": (o.text_embeds if proj else o.pooler_output).half()}
+    return out
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)  # summation order of the CPU kernels is part of the pin
+    if len(sys.argv) > 1 and sys.argv[1] == "clip":
+        out = Path(__file__).with_name("r02_clip_golden.pt")
+        torch.save(clip_case(), out)
+        print(out, out.stat().st_size, "bytes")
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "vae":
         out = Path(__file__).with_name("r02_vae_golden.pt")
         torch.save({"vae": vae_case(), "torch": torch.__version__}, out)
