@@ -1,4 +1,5 @@
-"""Components that sit either side of the hot path and stay on the reference path (text encoders, VAE).
+"""Shape-only stand-ins for components either side of the hot path (since round 2 only fall-backs: the native VAE
+decoder of vae.py and the native CLIP text towers of text_encoder.py are the defaults of every solver).
 
 The reference takes them from the diffusers pipeline: `pipe.tokenizer/text_encoder` (latent_diffusion.py:65-66,
 latent_sdxl.py:46-49) and `pipe.vae` / `madebyollin/sdxl-vae-fp16-fix` (latent_diffusion.py:64, latent_sdxl.py:44).
