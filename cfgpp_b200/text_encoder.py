@@ -212,6 +212,16 @@ class ClipConditioner:
         hidden, last, pooled = self.encoder.encode(ids, skip=skip, want_hidden=True, want_last=not proj, want_pooled=proj)
         return hidden, (pooled if proj else last)   # output[0]: text_embeds | last_hidden_state
 
+    def encode_batch(self, prompts: Sequence[str], clip_skip: Optional[int] = None, chunk: int = 16):
+        """Many prompts per call (the 64-prompt runs of examples/text_to_mscoco.py): one native encode per `chunk`
+        prompts instead of one per prompt; row i equals `self(prompts[i])`."""
+        hs, ps = [], []
+        for i in range(0, len(prompts), chunk):
+            h, p = self(list(prompts[i:i + chunk]), clip_skip=clip_skip)
+            hs.append(h)
+            ps.append(p)
+        return torch.cat(hs), (torch.cat(ps) if ps and ps[0] is not None else None)
+
 
 _ENCODERS: Dict[tuple, NativeCLIPTextEncoder] = {}
 

@@ -151,6 +151,13 @@ def test_conditioners_feed_the_solvers():
     assert torch.equal(c[:, :5], c2[:, :5]) and not torch.equal(c[:, 5], c2[:, 5])
     _, c3, _, _ = s.get_text_embed("", "a photo of a cat", "", "a photo of a cat", clip_skip=1)
     assert not torch.equal(c, c3)
+    # many prompts per call: row i of the batched encode == the single-prompt result
+    prompts = [f"a photo of object number {i} " + "very " * (i % 7) + "nice" for i in range(37)] + [""]
+    hb, pb = s.text_enc_2.encode_batch(prompts)
+    assert hb.shape == (38, 77, s.text_enc_2.encoder.cfg.hidden_size) and pb.shape == (38, s.cfg.pooled_dim)
+    for i in (0, 15, 16, 36, 37):
+        h1, p1 = s.text_enc_2(prompts[i])
+        assert rel_l2(hb[i:i + 1], h1) <= 1e-3 and rel_l2(pb[i:i + 1], p1) <= 1e-3
     d = LD.get_solver("ddim_cfg++", solver_config=SimpleNamespace(num_sampling=4), device="cuda:0",
                       unet_config=tiny_sd15_config(), model_key="synthetic:7")
     assert isinstance(d.text_encoder, TE.ClipConditioner)
