@@ -137,12 +137,13 @@ def op_layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: 
 
 
 def op_cfgpp_step(eps_uc: torch.Tensor, eps_c: torch.Tensor, method: int, coef, z: torch.Tensor,
-                  aux: torch.Tensor | None = None, want_z0t: bool = True):
-    """In-place CFG++ update of z (fp32 or fp16 state) from given eps; returns z0t (or None)."""
+                  aux: torch.Tensor | None = None, want_z0t: bool = True, noise: torch.Tensor | None = None):
+    """In-place CFG++ update of z (fp32 or fp16 state) from given eps; returns z0t (or None). `noise`: fp16 table
+    [slots, *z.shape] of the ancestral samplers (slot = coef.c3)."""
     from ctypes import byref
     lib = load()
     z0t = torch.empty_like(z) if want_z0t else None
     code = 0 if z.dtype == torch.float16 else 1
     check(lib.cfgpp_op_cfgpp_step(ptr(eps_uc), ptr(eps_c), c_int(z.numel()), c_int(method), c_int(code), byref(coef),
-                                  ptr(z), ptr(aux), ptr(z0t), stream_ptr()))
+                                  ptr(z), ptr(aux), ptr(z0t), ptr(noise), stream_ptr()))
     return z0t

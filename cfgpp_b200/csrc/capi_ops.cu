@@ -95,16 +95,20 @@ CFGPP_API int cfgpp_op_layernorm(const void* x, int M, int C, const void* gamma,
 }
 
 CFGPP_API int cfgpp_op_cfgpp_step(const void* eps_uc, const void* eps_c, int n, int method, int state_dtype,
-                                  const cfgpp_step_coef* coef_host, void* z, void* aux, void* z0t_out, void* stream) {
+                                  const cfgpp_step_coef* coef_host, void* z, void* aux, void* z0t_out,
+                                  const void* noise_dev, void* stream) {
   return guarded([&] {
     static_assert(sizeof(cfgpp_step_coef) == sizeof(StepCoef), "ABI struct mismatch");
+    static_assert(sizeof(StepCoef) % sizeof(void*) == 0, "the noise word is stored right behind the coefficients");
     StepCoef* coef_dev = nullptr;
-    CFGPP_CHECK_CUDA(cudaMalloc(&coef_dev, sizeof(StepCoef)));
+    CFGPP_CHECK_CUDA(cudaMalloc(&coef_dev, sizeof(StepCoef) + sizeof(void*)));
+    const __half** slot = reinterpret_cast<const __half**>(coef_dev + 1);
     cudaError_t e = cudaMemcpy(coef_dev, coef_host, sizeof(StepCoef), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(slot, &noise_dev, sizeof(void*), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
       try {
         run_step_only((const __half*)eps_uc, (const __half*)eps_c, n, method | (state_dtype == CFGPP_F16 ? 0x100 : 0),
-                      coef_dev, z, aux, z0t_out, (cudaStream_t)stream);
+                      coef_dev, z, aux, z0t_out, (cudaStream_t)stream, slot);
       } catch (...) {
         cudaFree(coef_dev);
         throw;

@@ -203,8 +203,8 @@ CFGPP_DEVICE float rs(float x) {  // round to the state dtype
 }
 
 template <bool kHalfState>
-CFGPP_DEVICE void cfgpp_update(int mode, const StepCoef& k, float eu, float ec, float z, float old_d, float& z_new,
-                               float& z0t, float& new_old) {
+CFGPP_DEVICE void cfgpp_update(int mode, const StepCoef& k, float eu, float ec, float z, float old_d, float noise,
+                               float& z_new, float& z0t, float& new_old) {
   // noise_pred = eps_uc + lambda * (eps_c - eps_uc)   (three fp16 tensor ops)
   const float np = rh(__fadd_rn(eu, rh(__fmul_rn(k.lambda, rh(__fsub_rn(ec, eu))))));
   new_old = 0.f;
@@ -222,12 +222,34 @@ CFGPP_DEVICE void cfgpp_update(int mode, const StepCoef& k, float eu, float ec, 
     // ud = x - sigma eps_uc.  k.second_order bits: 1 = second-order (2M) branch; 2 = EXTRAPOLATE with the guided
     // estimate instead of the unconditional one (plain-CFG euler / dpm++_2m: latent_diffusion.py:326-330, :470-487);
     // 4 = the 2M difference term uses the guided estimate (SD v1.5 `dpm++_2m_cfg++`, latent_diffusion.py:863, whereas
-    // SDXL's `dpm++_2m_cfgpp` uses the unconditional one, latent_sdxl.py:916).
+    // SDXL's `dpm++_2m_cfgpp` uses the unconditional one, latent_sdxl.py:916);
+    // 8 = ancestral: add noise * sigma_up (d3) after the update (euler_a, dpm++_2s_a: latent_diffusion.py:757-760, :823);
+    // 16 / 32 = the two UNet calls of a DPM-Solver++(2S) step (latent_diffusion.py:796-821): 16 parks x in `aux` and
+    // leaves the midpoint x_2 as the state the next replay feeds to the UNet, 32 combines the midpoint estimates with
+    // the parked x.
     const float den = rs<kHalfState>(__fadd_rn(z, rh(__fmul_rn(k.c0, np))));
     const float ud = rs<kHalfState>(__fadd_rn(z, rh(__fmul_rn(k.c0, eu))));
     const float ex = (k.second_order & 2) ? den : ud;
     z0t = den;
-    if (!(k.second_order & 1)) {
+    new_old = ex;
+    if (k.second_order & 16) {
+      // x_2 = (sigma_s / sigma_t) * x - expm1(-h r) * extrap
+      const float a = rs<kHalfState>(__fmul_rn(k.d0, z));
+      const float b = rs<kHalfState>(__fmul_rn(k.d1, ex));
+      z_new = rs<kHalfState>(__fsub_rn(a, b));
+      new_old = z;
+    } else if (k.second_order & 32) {
+      const float xr = rs<kHalfState>(__fmul_rn(k.d1, old_d));  // (sigma_down / sigma_t) * x, x parked by the midpoint call
+      if (k.second_order & 2) {
+        // plain CFG: x = ratio * x - expm1(-h) * denoised_2
+        z_new = rs<kHalfState>(__fsub_rn(xr, rs<kHalfState>(__fmul_rn(k.d2, den))));
+      } else {
+        // CFG++: x = denoised_2 - exp(-h) * uncond_denoised_2 + ratio * x
+        const float t1 = rs<kHalfState>(__fmul_rn(k.d0, ud));
+        z_new = rs<kHalfState>(__fadd_rn(rs<kHalfState>(__fsub_rn(den, t1)), xr));
+      }
+      new_old = old_d;
+    } else if (!(k.second_order & 1)) {
       float d = rs<kHalfState>(__fsub_rn(z, ex));
       d = rs<kHalfState>(__fmul_rn(d, k.c1));  // / sigma_i  (scalar divisor -> reciprocal multiply on CUDA)
       d = rs<kHalfState>(__fmul_rn(d, k.c2));  // * sigma_{i+1}
@@ -241,7 +263,7 @@ CFGPP_DEVICE void cfgpp_update(int mode, const StepCoef& k, float eu, float ec, 
       const float extra2 = rs<kHalfState>(__fmul_rn(k.d3, z));
       z_new = rs<kHalfState>(__fadd_rn(rs<kHalfState>(__fadd_rn(den, extra1)), extra2));
     }
-    new_old = ex;
+    if (k.second_order & 8) z_new = rs<kHalfState>(__fadd_rn(z_new, rs<kHalfState>(__fmul_rn(noise, k.d3))));
   }
 }
 
@@ -256,15 +278,23 @@ CFGPP_DEVICE void store_state(void* p, size_t i, bool is_half, float v) {
 }
 
 CFGPP_DEVICE void apply_step_elem(int mode, int half_state, const StepCoef& k, float eu, float ec, void* z, void* aux,
-                                  void* z0t_out, size_t i) {
+                                  void* z0t_out, const __half* const* noise_slot, size_t n, size_t i) {
   const bool hs = half_state != 0;
   const float zv = load_state(z, i, hs);
-  const float old_d = (mode == STEP_DPMPP2M_CFGPP && (k.second_order & 1)) ? load_state(aux, i, hs) : 0.f;
+  const bool kd = mode == STEP_DPMPP2M_CFGPP;
+  const float old_d = (kd && (k.second_order & (1 | 32))) ? load_state(aux, i, hs) : 0.f;
+  float noise = 0.f;
+  if (kd && (k.second_order & 8) && noise_slot) {
+    // slot index travels in c3 (exact for any realistic step count); the base pointer lives in device memory so the
+    // captured graph survives a re-allocation of the noise table
+    const __half* base = *noise_slot;
+    if (base) noise = __half2float(base[static_cast<size_t>(k.c3) * n + i]);
+  }
   float zn, z0, no;
   if (hs)
-    cfgpp_update<true>(mode, k, eu, ec, zv, old_d, zn, z0, no);
+    cfgpp_update<true>(mode, k, eu, ec, zv, old_d, noise, zn, z0, no);
   else
-    cfgpp_update<false>(mode, k, eu, ec, zv, old_d, zn, z0, no);
+    cfgpp_update<false>(mode, k, eu, ec, zv, old_d, noise, zn, z0, no);
   store_state(z, i, hs, zn);
   if (z0t_out) store_state(z0t_out, i, hs, z0);
   if (mode == STEP_DPMPP2M_CFGPP && aux) store_state(aux, i, hs, no);
@@ -274,7 +304,8 @@ CFGPP_DEVICE void apply_step_elem(int mode, int half_state, const StepCoef& k, f
 __global__ void conv_out_step_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
                                      const __half* __restrict__ bias, int B, int H, int W, int Cin, int mode,
                                      int half_state, const StepCoef* __restrict__ coef, void* z, void* aux,
-                                     void* z0t_out, __half* __restrict__ eps_uc, __half* __restrict__ eps_c) {
+                                     void* z0t_out, __half* __restrict__ eps_uc, __half* __restrict__ eps_c,
+                                     const __half* const* __restrict__ noise_slot) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ __half swh[];  // [4][9][Cin]
@@ -340,17 +371,19 @@ __global__ void conv_out_step_kernel(const __half* __restrict__ x, const __half*
     const size_t i = (static_cast<size_t>(b) * 4 + lane) * HW + r;  // NCHW latent index
     if (eps_uc) eps_uc[i] = __float2half_rn(eu);
     if (eps_c) eps_c[i] = __float2half_rn(ec);
-    if (mode != STEP_NONE) apply_step_elem(mode, half_state, *coef, eu, ec, z, aux, z0t_out, i);
+    if (mode != STEP_NONE)
+      apply_step_elem(mode, half_state, *coef, eu, ec, z, aux, z0t_out, noise_slot, static_cast<size_t>(B) * 4 * HW, i);
   }
 }
 
 __global__ void step_only_kernel(const __half* __restrict__ eps_uc, const __half* __restrict__ eps_c, int n, int mode,
-                                 int half_state, const StepCoef* __restrict__ coef, void* z, void* aux, void* z0t_out) {
+                                 int half_state, const StepCoef* __restrict__ coef, void* z, void* aux, void* z0t_out,
+                                 const __half* const* __restrict__ noise_slot) {
   pdl_launch_dependents();
   pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  apply_step_elem(mode, half_state, *coef, __half2float(eps_uc[i]), __half2float(eps_c[i]), z, aux, z0t_out, i);
+  apply_step_elem(mode, half_state, *coef, __half2float(eps_uc[i]), __half2float(eps_c[i]), z, aux, z0t_out, noise_slot, n, i);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -440,7 +473,7 @@ void run_conv_in(const void* z, int z_is_half, const float* in_scale, const __ha
 // The state dtype travels in bit 8 of `mode` (mode | 0x100 = fp16 sampler state).
 void run_conv_out_step(const __half* x, const __half* w, const __half* bias, int B, int H, int W, int Cin, int mode,
                        const StepCoef* coef_dev, void* z, void* aux, void* z0t_out, __half* eps_uc, __half* eps_c,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const __half* const* noise_slot) {
   CFGPP_REQUIRE(Cin % 8 == 0, "conv_out Cin must be a multiple of 8");
   const int half_state = (mode & 0x100) ? 1 : 0;
   const int m = mode & 0xff;
@@ -449,14 +482,14 @@ void run_conv_out_step(const __half* x, const __half* w, const __half* bias, int
   const int warps = 8;
   const int total = B * H * W;
   launch_pdl(conv_out_step_kernel, dim3((total + warps - 1) / warps), dim3(warps * 32), smem, stream, 
-      x, w, bias, B, H, W, Cin, m, half_state, coef_dev, z, aux, z0t_out, eps_uc, eps_c);
+      x, w, bias, B, H, W, Cin, m, half_state, coef_dev, z, aux, z0t_out, eps_uc, eps_c, noise_slot);
 }
 
 void run_step_only(const __half* eps_uc, const __half* eps_c, int n, int mode, const StepCoef* coef_dev, void* z,
-                   void* aux, void* z0t_out, cudaStream_t stream) {
+                   void* aux, void* z0t_out, cudaStream_t stream, const __half* const* noise_slot) {
   const int half_state = (mode & 0x100) ? 1 : 0;
   launch_pdl(step_only_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, eps_uc, eps_c, n, mode & 0xff, half_state, coef_dev, z, aux,
-                                                        z0t_out);
+                                                        z0t_out, noise_slot);
 }
 
 void run_upsample2x(const __half* x, __half* out, int B, int H, int W, int C, cudaStream_t stream) {

@@ -52,7 +52,10 @@ struct StepCoef {  // per-step scalars, computed on the host in fp32 exactly as 
   float d0, d1, d2;      // DPM++ 2M branch: -exp(-h), expm1(-h), 1/(2r) ; d3 = exp(-h)
   float d3;
   int second_order;      // DPM++ / Euler family bits: 1 = 2M update (else Euler), 2 = extrapolate with the guided
-                         // estimate (plain CFG), 4 = 2M difference term on the guided estimate (SD v1.5 dpm++_2m_cfg++)
+                         // estimate (plain CFG), 4 = 2M difference term on the guided estimate (SD v1.5 dpm++_2m_cfg++),
+                         // 8 = ancestral noise: + noise[slot c3] * d3 (sigma_up), 16 / 32 = midpoint / final call of a
+                         // DPM-Solver++(2S) step (16: d0 = sigma_s / sigma_t, d1 = expm1(-h r); 32: d0 = exp(-h),
+                         // d1 = sigma_down / sigma_t, d2 = expm1(-h))
 };
 
 // One sampler step's device-resident scalars; a table of these lives in HBM and a 1-thread kernel selects the
@@ -65,14 +68,16 @@ struct StepState {
 void run_select_step(const StepState* table, int* counter, StepState* cur, cudaStream_t stream);
 
 // conv_out 3x3 (Cin -> 4) on the GroupNorm+SiLU'ed NHWC input x [2B,H,W,Cin] fused with the CFG++ guidance mix and
-// the scheduler update. z is the sampler state (NCHW, fp32 for DDIM modes, fp16 for DPM++), updated in place.
+// the scheduler update. noise_slot (may be null): device word holding the base of the ancestral noise table
+// [slots][B,4,H,W] fp16. z is the sampler state (NCHW, fp32 for DDIM modes, fp16 for DPM++), updated in place.
 void run_conv_out_step(const __half* x, const __half* w /*[4][9][Cin]*/, const __half* bias, int B, int H, int W,
                        int Cin, int mode, const StepCoef* coef_dev, void* z, void* aux /*old_denoised*/,
-                       void* z0t_out, __half* eps_uc, __half* eps_c, cudaStream_t stream);
+                       void* z0t_out, __half* eps_uc, __half* eps_c, cudaStream_t stream,
+                       const __half* const* noise_slot = nullptr);
 
 // standalone fused CFG++ update from given eps (used when a per-step callback needs the un-fused seam)
 void run_step_only(const __half* eps_uc, const __half* eps_c, int n, int mode, const StepCoef* coef_dev, void* z,
-                   void* aux, void* z0t_out, cudaStream_t stream);
+                   void* aux, void* z0t_out, cudaStream_t stream, const __half* const* noise_slot = nullptr);
 
 void run_upsample2x(const __half* x, __half* out, int B, int H, int W, int C, cudaStream_t stream);
 // stride-2 pad-1 3x3 im2col: x [B,H,W,C] -> out [B*(H/2)*(W/2), 9*C] (tap-major, matches the packed weight)

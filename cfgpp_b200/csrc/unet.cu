@@ -144,6 +144,7 @@ Unet::~Unet() {
   for (auto& kv : raw_) cudaFree(kv.second.p);
   for (void* p : weight_allocs_) cudaFree(p);
   for (void* p : act_allocs_) cudaFree(p);
+  if (noise_buf_) cudaFree(noise_buf_);
   streamk_free(sk_ws_, sk_flags_);
 }
 
@@ -729,6 +730,8 @@ void Unet::prepare(int batch, int h_lat, int w_lat) {
       z_state_ = alloc_bytes(lat * sizeof(float));
       aux_state_ = alloc_bytes(lat * sizeof(float));
       z0t_state_ = alloc_bytes(lat * sizeof(float));
+      noise_slot_ = static_cast<const __half**>(alloc_bytes(sizeof(__half*)));
+      CFGPP_CHECK_CUDA(cudaMemcpy(noise_slot_, &noise_buf_, sizeof(__half*), cudaMemcpyHostToDevice));
       fwd_eps_uc_ = alloc_act(lat);
       fwd_eps_c_ = alloc_act(lat);
       temb_w_all_ = packed_cat_rows(temb_w_keys);
@@ -1058,6 +1061,23 @@ void Unet::set_state(const void* z, int z_dtype, cudaStream_t stream) {
   CFGPP_CHECK_CUDA(cudaMemcpyAsync(z_state_, z, lat * es, cudaMemcpyDeviceToDevice, stream));
 }
 
+void Unet::set_noise(const __half* noise, int slots, cudaStream_t stream) {
+  CFGPP_REQUIRE(prepared_, "call cfgpp_prepare first");
+  CFGPP_REQUIRE(noise != nullptr && slots >= 1 && slots <= 1024, "noise table: 1..1024 slots");
+  const size_t n = static_cast<size_t>(slots) * B_ * 4 * H_ * W_;
+  if (n > noise_cap_) {
+    CFGPP_CHECK_CUDA(cudaStreamSynchronize(stream));  // a replay in flight may still read the old table
+    if (noise_buf_) cudaFree(noise_buf_);
+    noise_buf_ = nullptr;
+    noise_cap_ = 0;
+    CFGPP_CHECK_CUDA(cudaMalloc(&noise_buf_, n * sizeof(__half)));
+    noise_cap_ = n;
+    CFGPP_CHECK_CUDA(cudaMemcpyAsync(noise_slot_, &noise_buf_, sizeof(__half*), cudaMemcpyHostToDevice, stream));
+    CFGPP_CHECK_CUDA(cudaStreamSynchronize(stream));  // &noise_buf_ is host memory of this object: do not let it race
+  }
+  CFGPP_CHECK_CUDA(cudaMemcpyAsync(noise_buf_, noise, n * sizeof(__half), cudaMemcpyDeviceToDevice, stream));
+}
+
 void Unet::ensure_graph(cudaStream_t stream) {
   if (graph_valid_) return;
   if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
@@ -1071,7 +1091,7 @@ void Unet::ensure_graph(cudaStream_t stream) {
                 conv_in_out_, B_, H_, W_, d_.block_out_channels[0], 2, capture_stream_);
     run_body(capture_stream_, true);
     run_conv_out_step(final_norm_.p, conv_out_w_, conv_out_b_, B_, H_, W_, final_norm_.C, mode, &cur_state_->coef,
-                      z_state_, aux_state_, z0t_state_, nullptr, nullptr, capture_stream_);
+                      z_state_, aux_state_, z0t_state_, nullptr, nullptr, capture_stream_, noise_slot_);
   } catch (...) {
     cudaGraph_t g = nullptr;
     cudaStreamEndCapture(capture_stream_, &g);
@@ -1103,7 +1123,7 @@ void Unet::apply_step(int step, const __half* eps_uc, const __half* eps_c, cudaS
   CFGPP_REQUIRE(prepared_ && step >= 0 && step < nsteps_, "step outside the schedule");
   const int mode = method_ | (state_dtype_ == CFGPP_F16 ? 0x100 : 0);
   const int n = B_ * 4 * H_ * W_;
-  run_step_only(eps_uc, eps_c, n, mode, &step_table_[step].coef, z_state_, aux_state_, z0t_state_, stream);
+  run_step_only(eps_uc, eps_c, n, mode, &step_table_[step].coef, z_state_, aux_state_, z0t_state_, stream, noise_slot_);
 }
 
 }  // namespace cfgpp

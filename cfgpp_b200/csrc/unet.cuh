@@ -53,6 +53,8 @@ class Unet {
                     cudaStream_t stream);
   void set_schedule(int method, int state_dtype, const cfgpp_step_state* steps, int nsteps, cudaStream_t stream);
   void set_state(const void* z, int z_dtype, cudaStream_t stream);
+  // ancestral samplers: fp16 noise table [slots][B,4,H,W] (device), copied into a handle-owned buffer
+  void set_noise(const __half* noise, int slots, cudaStream_t stream);
   void run_steps(int first_step, int nsteps, cudaStream_t stream);
   void get_state(int which, void* out, cudaStream_t stream);
   void apply_step(int step, const __half* eps_uc, const __half* eps_c, cudaStream_t stream);
@@ -167,6 +169,9 @@ class Unet {
   void* z_state_ = nullptr;   // (B,4,H,W) fp32-sized buffer (holds fp16 or fp32)
   void* aux_state_ = nullptr;
   void* z0t_state_ = nullptr;
+  const __half** noise_slot_ = nullptr;  // device word holding noise_buf_ (read by the step kernel: graph-stable)
+  __half* noise_buf_ = nullptr;          // owned, survives prepare(); re-allocated when a larger table arrives
+  size_t noise_cap_ = 0;                 // elements
   const void* fwd_z_ = nullptr;  // input of the un-fused forward
   int fwd_z_dtype_ = CFGPP_F32;
   __half *fwd_eps_uc_ = nullptr, *fwd_eps_c_ = nullptr;

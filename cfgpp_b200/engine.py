@@ -181,6 +181,13 @@ class NativeUNet:
         with torch.cuda.device(self.device):
             nv.check(self.lib.cfgpp_set_state(self._h, nv.ptr(z), c_int(_dtype_code(z)), nv.stream_ptr()))
 
+    def set_noise(self, noise: torch.Tensor):
+        """Ancestral samplers: fp16 noise table (slots, batch, 4, h, w), one slot per step that adds fresh noise."""
+        noise = noise.to(self.device, torch.float16).contiguous()
+        assert noise.dim() == 5 and tuple(noise.shape[1:]) == (self.batch, 4, *self.latent_hw), "noise table shape"
+        with torch.cuda.device(self.device):
+            nv.check(self.lib.cfgpp_set_noise(self._h, nv.ptr(noise), c_int(noise.shape[0]), nv.stream_ptr()))
+
     def run_steps(self, first: int = 0, n: Optional[int] = None):
         n = self._nsteps - first if n is None else n
         with torch.cuda.device(self.device):

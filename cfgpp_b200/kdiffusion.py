@@ -87,6 +87,24 @@ def _fused_trajectory(solver, x, steps, cond):
     return eng.get_state(1), eng.get_state(0)
 
 
+def _fused_ancestral_trajectory(solver, x, sigmas, cfg_guidance, cond, cfgpp: bool, two_s: bool):
+    """Ancestral loops on the fused step kernel: the fresh noise of every step is drawn up front, in loop order, with
+    the calls the op-by-op loop would make (`torch.randn_like(x)`, same generator state => same values), and travels
+    as a table the step kernel indexes; dpm++_2s_a replays the graph twice per step (midpoint, final)."""
+    from . import schedule as S
+    steps, slots = S.kd_ancestral_steps(sigmas, solver.timestep, cfg_guidance, cfgpp, two_s)
+    solver._prepare(x, *cond, force=True)
+    eng = solver.unet
+    state0 = x.to(eng.device, torch.float16)
+    noise = torch.stack([torch.randn_like(state0) for _ in range(slots)]) if slots else None
+    eng.set_schedule(S.STEP_DPMPP2M_CFGPP, torch.float16, steps)
+    eng.set_state(state0)
+    if noise is not None:
+        eng.set_noise(noise)
+    eng.run_steps(0, len(steps))
+    return eng.get_state(1), eng.get_state(0)
+
+
 def _fusable(solver, callback_fn) -> bool:
     """Deterministic loops without a callback run fused when the solver sits on the native engine (the CPU tests drive
     these loops with a stand-in UNet and keep the op-by-op torch form, which stays the specification)."""
@@ -108,7 +126,9 @@ def euler_cfgpp_loop(solver: KDiffusionMixin, x, sigmas, cfg_guidance, cond, cal
     latent_diffusion.py:699-719 (euler_cfg++), :744-762 (euler_a_cfg++), latent_sdxl.py:787-808 (SDXL euler_cfg++).
     Returns (last denoised, x). `adopt_callback`: the ancestral variant of the reference ignores what the callback
     returns (:757-762). `cfgpp=False`: plain CFG, the derivative uses the guided estimate (:326-330, :372-379)."""
-    if not ancestral and _fusable(solver, callback_fn):
+    if _fusable(solver, callback_fn):
+        if ancestral:
+            return _fused_ancestral_trajectory(solver, x, sigmas, cfg_guidance, cond, cfgpp, two_s=False)
         from . import schedule as S
         return _fused_trajectory(solver, x, S.kd_steps(sigmas, solver.timestep, cfg_guidance, cfgpp), cond)
     denoised = None
@@ -136,6 +156,8 @@ def dpmpp_2s_a_cfgpp_loop(solver: KDiffusionMixin, x, sigmas, cfg_guidance, cond
     """DPM-Solver++(2S) ancestral, CFG++: both the midpoint and the final update extrapolate with the unconditional
     Tweedie estimate — latent_diffusion.py:782-825 (two UNet calls per step). `cfgpp=False`: the plain-CFG original
     (:408-437), guided estimate everywhere and the standard final update."""
+    if _fusable(solver, callback_fn):
+        return _fused_ancestral_trajectory(solver, x, sigmas, cfg_guidance, cond, cfgpp, two_s=True)
     t_fn = lambda s: s.log().neg()      # noqa: E731
     sigma_fn = lambda t: t.neg().exp()  # noqa: E731
     denoised = None

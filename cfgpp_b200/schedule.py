@@ -157,6 +157,7 @@ def dpmpp_2m_cfgpp_steps(sch: Schedule, cfg_guidance: float):
 
 
 KD_SECOND_ORDER, KD_EXTRAP_GUIDED, KD_DIFF_GUIDED = 1, 2, 4   # cfgpp_step_coef.second_order bits
+KD_NOISE, KD_2S_MID, KD_2S_FINAL = 8, 16, 32
 
 
 def kd_steps(sigmas: torch.Tensor, timestep_fn, cfg_guidance: float, cfgpp: bool, second_order: bool = False,
@@ -184,6 +185,54 @@ def kd_steps(sigmas: torch.Tensor, timestep_fn, cfg_guidance: float, cfgpp: bool
             out.append(_state(t, in_scale, cfg_guidance, c=c, d=(-torch.exp(-h), (-h).expm1(), one / (2 * r), torch.exp(-h)),
                               second_order=base | KD_SECOND_ORDER | (KD_DIFF_GUIDED if diff_guided else 0)))
     return out
+
+
+def _ancestral_step(sigma_from, sigma_to, eta: float = 1.):
+    """(sigma_down, sigma_up) — latent_diffusion.py:30-37 (same arithmetic on the same 0-dim tensors)."""
+    if not eta:
+        return sigma_to, 0.
+    var_ratio = sigma_to ** 2 * (sigma_from ** 2 - sigma_to ** 2) / sigma_from ** 2
+    sigma_up = min(sigma_to, eta * var_ratio ** 0.5)
+    return (sigma_to ** 2 - sigma_up ** 2) ** 0.5, sigma_up
+
+
+def kd_ancestral_steps(sigmas: torch.Tensor, timestep_fn, cfg_guidance: float, cfgpp: bool, two_s: bool = False):
+    """Schedule entries of the ancestral VE-cast loops for the fused step kernel. Returns (entries, noise_slots):
+    `euler_a(_cfg++)` (latent_diffusion.py:344-379 / :744-762): one entry per step, x' = den + d * sigma_down
+    + noise * sigma_up; `dpm++_2s_a(_cfg++)` (:408-437 / :782-825, two_s=True): two entries (midpoint call, final
+    call) per step with sigma_down > 0, the Euler form otherwise. A step with sigma_{i+1} > 0 consumes one noise slot,
+    in loop order — the caller draws `noise_slots` tensors with `torch.randn_like` up front, which is the very
+    sequence the reference's loop would draw."""
+    t_fn = lambda sg: sg.log().neg()    # noqa: E731
+    sigma_fn = lambda t: t.neg().exp()  # noqa: E731
+    one = torch.tensor(1.0, dtype=torch.float32)
+    base = 0 if cfgpp else KD_EXTRAP_GUIDED
+    out, slot = [], 0
+    for i in range(len(sigmas) - 1):
+        sigma = sigmas[i]
+        in_scale = one / (sigma ** 2 + 1) ** 0.5
+        inv_sigma = one / torch.tensor(sigma.item(), dtype=torch.float32)
+        t = float(timestep_fn(sigma))
+        sigma_down, sigma_up = _ancestral_step(sigmas[i], sigmas[i + 1])
+        noisy = bool(sigmas[i + 1] > 0)
+        nbits = KD_NOISE if noisy else 0
+        if not two_s or sigma_down == 0:
+            out.append(_state(t, in_scale, cfg_guidance, c=(-sigma.clone(), inv_sigma, sigma_down, slot),
+                              d=(0, 0, 0, sigma_up if noisy else 0.0), second_order=base | nbits))
+        else:
+            tt, t_next = t_fn(sigmas[i]), t_fn(sigma_down)
+            r = 1 / 2
+            h = t_next - tt
+            s = tt + r * h
+            sigma_s = sigma_fn(s)
+            out.append(_state(t, in_scale, cfg_guidance, c=(-sigma.clone(), inv_sigma, 0.0, 0.0),
+                              d=(sigma_fn(s) / sigma_fn(tt), (-h * r).expm1(), 0, 0), second_order=base | KD_2S_MID))
+            out.append(_state(float(timestep_fn(sigma_s)), one / (sigma_s ** 2 + 1) ** 0.5, cfg_guidance,
+                              c=(-sigma_s.clone(), 0.0, 0.0, slot),
+                              d=(torch.exp(-h), sigma_fn(t_next) / sigma_fn(tt), (-h).expm1(), sigma_up if noisy else 0.0),
+                              second_order=base | KD_2S_FINAL | nbits))
+        slot += 1 if noisy else 0
+    return out, slot
 
 
 def to_c_array(steps: List[StepStateC]):

@@ -69,7 +69,13 @@ typedef struct cfgpp_step_coef {
   float d0, d1, d2, d3;  /* DPM++2M 2nd-order branch: -exp(-h), expm1(-h), 1/(2r), exp(-h) */
   int second_order;      /* VE-cast family bits: 1 = 2M update (else the Euler-CFG++ update: first step / sigma_next == 0 /
                             euler solvers), 2 = extrapolate with the guided estimate (plain-CFG euler, dpm++_2m),
-                            4 = 2M difference term on the guided estimate (SD v1.5 dpm++_2m_cfg++) */
+                            4 = 2M difference term on the guided estimate (SD v1.5 dpm++_2m_cfg++),
+                            8 = ancestral (euler_a, dpm++_2s_a: latent_diffusion.py:757-760, :823): after the update add
+                                noise[slot c3] * d3 (sigma_up), the table comes from cfgpp_set_noise,
+                            16 / 32 = the two UNet calls of a DPM-Solver++(2S) step (latent_diffusion.py:796-821), one
+                                schedule entry each: 16 = midpoint, d0 = sigma_s / sigma_t, d1 = expm1(-h r) (x is parked,
+                                the state becomes x_2); 32 = final, d0 = exp(-h), d1 = sigma_down / sigma_t,
+                                d2 = expm1(-h) (plain-CFG form when bit 2 is set) */
 } cfgpp_step_coef;
 
 typedef struct cfgpp_step_state {
@@ -130,6 +136,9 @@ int cfgpp_set_schedule(cfgpp_handle* h, int method, int state_dtype, const cfgpp
                        void* stream);
 /* Copy the caller's initial state into the library's state buffer (z: zT / x0; aux: old_denoised or NULL). */
 int cfgpp_set_state(cfgpp_handle* h, const void* z_dev, int z_dtype, void* stream);
+/* Ancestral samplers: the trajectory's fresh noise, drawn up front in the order the reference's loop would draw it
+ * (`torch.randn_like(x)` once per step with sigma_next > 0). noise_dev: fp16 [slots][batch,4,h,w]; copied. */
+int cfgpp_set_noise(cfgpp_handle* h, const void* noise_dev, int slots, void* stream);
 /* Run `nsteps` consecutive steps starting at schedule index `first_step` on the internal state. */
 int cfgpp_run_steps(cfgpp_handle* h, int first_step, int nsteps, void* stream);
 /* which: 0 = state z (same dtype as the state), 1 = z0t of the last executed step. */
@@ -213,8 +222,10 @@ int cfgpp_op_groupnorm(const void* x1, int C1, const void* x2, int C2, int B, in
                        const void* beta, float eps, int silu, void* out, void* stream);
 int cfgpp_op_layernorm(const void* x, int M, int C, const void* gamma, const void* beta, float eps, void* out,
                        void* stream);
+/* noise_dev (may be null): fp16 ancestral-noise table [slots][n]; the slot is coef_host->c3 (second_order bit 8). */
 int cfgpp_op_cfgpp_step(const void* eps_uc, const void* eps_c, int n, int method, int state_dtype,
-                        const cfgpp_step_coef* coef_host, void* z, void* aux, void* z0t_out, void* stream);
+                        const cfgpp_step_coef* coef_host, void* z, void* aux, void* z0t_out, const void* noise_dev,
+                        void* stream);
 
 #ifdef __cplusplus
 }

@@ -436,3 +436,93 @@ def test_step_kernel_kdiffusion_family_matches_reference_arithmetic():
                 x = xr
                 xs.copy_(xr)
                 aux.copy_(ex)
+
+
+def test_step_kernel_ancestral_family_matches_reference_arithmetic():
+    """Selector bits 8 / 16 / 32 of the fused VE-cast step: the ancestral Euler update and the two calls of a
+    DPM-Solver++(2S) ancestral step (latent_diffusion.py:744-762, :782-825; plain forms :372-379, :408-437) against the
+    torch ops of kdiffusion.py on the same eps and the same pre-drawn noise, <= 2 fp16 ulp per call (teacher-forced)."""
+    from cfgpp_b200 import _native as nv, kdiffusion as K, schedule as S
+    g = torch.Generator().manual_seed(9)
+    sigmas = K.get_sigmas_karras(6, 0.03, 14.6, rho=7.)
+    timestep_fn = lambda s: torch.tensor(500)  # noqa: E731 — irrelevant for the update arithmetic
+    t_fn = lambda s: s.log().neg()      # noqa: E731
+    sigma_fn = lambda t: t.neg().exp()  # noqa: E731
+    shape = (2, 4, 16, 16)
+    draw = lambda: torch.randn(shape, generator=g).half().to(dev)  # noqa: E731
+    for cfgpp in (True, False):
+        for two_s in (False, True):
+            steps, slots = S.kd_ancestral_steps(sigmas, timestep_fn, 0.6, cfgpp, two_s)
+            assert slots == len(sigmas) - 2                       # every step but the last adds noise
+            assert len(steps) == (2 * (len(sigmas) - 2) + 1 if two_s else len(sigmas) - 1)
+            noise = torch.stack([draw() for _ in range(slots)])
+            x = (torch.randn(shape, generator=g) * sigmas[0]).half().to(dev)
+            xs, aux, k = x.clone(), torch.zeros_like(x), 0
+
+            def call(xin, sigma, coef, tag):
+                """One UNet call's worth of update on the native kernel and in torch; returns (den, ud)."""
+                eu, ec = draw(), draw()
+                npred = eu + 0.6 * (ec - eu)
+                z0 = nv.op_cfgpp_step(eu, ec, S.STEP_DPMPP2M_CFGPP, coef, xs, aux, noise=noise)
+                den, ud = xin - npred * sigma, xin - eu * sigma
+                assert ((z0.float() - den.float()).abs() <= 1 * _ulp16(den)).all(), tag
+                return den, ud
+
+            for i in range(len(sigmas) - 1):
+                tag = f"cfgpp={cfgpp} two_s={two_s} step {i}"
+                sigma_down, sigma_up = K.get_ancestral_step(sigmas[i], sigmas[i + 1])
+                if not two_s or sigma_down == 0:
+                    den, ud = call(x, sigmas[i], steps[k].coef, tag)
+                    k += 1
+                    ex = ud if cfgpp else den
+                    xr = den + (x - ex) / sigmas[i].item() * sigma_down
+                else:
+                    den, ud = call(x, sigmas[i], steps[k].coef, tag + " mid")
+                    ex = ud if cfgpp else den
+                    t, t_next = t_fn(sigmas[i]), t_fn(sigma_down)
+                    h = t_next - t
+                    s = t + 0.5 * h
+                    x_2 = (sigma_fn(s) / sigma_fn(t)) * x - (-h * 0.5).expm1() * ex
+                    assert ((xs.float() - x_2.float()).abs() <= 2 * _ulp16(x_2)).all(), tag + " x_2"
+                    assert torch.equal(aux, x), tag + " parked x"
+                    xs.copy_(x_2)
+                    den2, ud2 = call(x_2, sigma_fn(s), steps[k + 1].coef, tag + " final")
+                    k += 2
+                    if cfgpp:
+                        xr = den2 - torch.exp(-h) * ud2 + (sigma_fn(t_next) / sigma_fn(t)) * x
+                    else:
+                        xr = (sigma_fn(t_next) / sigma_fn(t)) * x - (-h).expm1() * den2
+                if sigmas[i + 1] > 0:
+                    xr = xr + noise[i] * sigma_up
+                assert ((xs.float() - xr.float()).abs() <= 2 * _ulp16(xr)).all(), tag
+                x = xr
+                xs.copy_(xr)
+            assert k == len(steps)
+
+
+@pytest.mark.parametrize("method", ["euler_a_cfg++", "dpm++_2s_a_cfg++", "euler_a", "dpm++_2s_a"])
+def test_ancestral_fused_trajectory_equals_callback_path(method):
+    """The ancestral samplers run as fused CUDA-graph trajectories (noise drawn up front); with a callback installed
+    they take the op-by-op loop over the `predict_noise` seam, drawing noise step by step. Same seed => the same noise
+    values, and the same state up to fp16 rounding-order noise of the last ulp."""
+    from cfgpp_b200 import latent_diffusion as LD
+    cfg, sd, net, ref = build_pair("tiny_sd15", dev)
+    net.close()
+    del ref
+    nfe, lam, hw = 6, 0.6, 32
+    z, uc, c, _ = make_inputs(cfg, 1, hw, dev)
+    solver = LD.get_solver(method, solver_config=SimpleNamespace(num_sampling=nfe), device=dev, unet_config=cfg,
+                           state_dict=sd)
+    x0 = (z * (solver.karras_sigmas()[0] ** 2 + 1) ** 0.5).half()
+    seen = []
+    torch.manual_seed(77)
+    d_cb, x_cb = solver.reverse_process(uc, c, lam, x0.clone(), callback_fn=lambda i, t, kw: (seen.append(i), kw)[1])
+    torch.manual_seed(77)
+    d_f, x_f = solver.reverse_process(uc, c, lam, x0.clone())
+    assert seen == list(range(nfe))
+    e_x, e_d = rel_l2(x_f, x_cb), rel_l2(d_f, d_cb)
+    print(f"{method}: fused vs callback path — final x {e_x:.3e}, last denoised {e_d:.3e}")
+    assert e_x <= 2e-3 and e_d <= 2e-3
+    torch.manual_seed(78)
+    _, x_other = solver.reverse_process(uc, c, lam, x0.clone())
+    assert rel_l2(x_other, x_f) > 1e-2        # a different seed really changes the injected noise

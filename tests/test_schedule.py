@@ -88,3 +88,33 @@ def test_sigma_to_t_quantized_and_interpolated():
     t = S.sigma_to_t(sch, mid[None], quantize=False)
     assert 200.0 < t.item() < 201.0 and abs(t.item() - 200.5) < 0.05
     assert S.sigma_to_t(sch, torch.tensor([1e6]), quantize=False).item() == 999.0   # clamped above the table
+
+
+def test_kd_ancestral_schedule_layout():
+    """euler_a: one entry per step; dpm++_2s_a: (midpoint, final) pairs while sigma_down > 0, the Euler form on the last
+    step; one noise slot per step with sigma_next > 0, numbered in loop order (latent_diffusion.py:744-762, :782-825)."""
+    from cfgpp_b200 import kdiffusion as K, schedule as S
+    sigmas = K.get_sigmas_karras(5, 0.03, 14.6, rho=7.)
+    tfn = lambda s: torch.tensor(321)  # noqa: E731
+    for cfgpp in (True, False):
+        base = 0 if cfgpp else S.KD_EXTRAP_GUIDED
+        steps, slots = S.kd_ancestral_steps(sigmas, tfn, 0.7, cfgpp, two_s=False)
+        assert slots == 4 and len(steps) == 5
+        for i, st in enumerate(steps):
+            down, up = K.get_ancestral_step(sigmas[i], sigmas[i + 1])
+            assert st.coef.second_order == base | (S.KD_NOISE if i < 4 else 0)
+            assert st.coef.c2 == pytest.approx(float(down)) and st.coef.d3 == pytest.approx(float(up) if i < 4 else 0.0)
+            assert st.coef.c0 == pytest.approx(-float(sigmas[i])) and (i == 4 or int(st.coef.c3) == i)
+        steps, slots = S.kd_ancestral_steps(sigmas, tfn, 0.7, cfgpp, two_s=True)
+        assert slots == 4 and len(steps) == 9
+        bits = [st.coef.second_order for st in steps]
+        assert bits == [base | S.KD_2S_MID, base | S.KD_2S_FINAL | S.KD_NOISE] * 4 + [base]
+        for i in range(4):
+            mid, fin = steps[2 * i], steps[2 * i + 1]
+            down, up = K.get_ancestral_step(sigmas[i], sigmas[i + 1])
+            h = -torch.log(down) + torch.log(sigmas[i])
+            assert fin.coef.d0 == pytest.approx(float(torch.exp(-h)), rel=1e-5)
+            assert fin.coef.d1 == pytest.approx(float(down / sigmas[i]), rel=1e-5) and int(fin.coef.c3) == i
+            sigma_s = float((sigmas[i] * down) ** 0.5)                  # geometric midpoint in log-sigma (r = 1/2)
+            assert -fin.coef.c0 == pytest.approx(sigma_s, rel=1e-5) and mid.coef.d0 == pytest.approx(sigma_s / float(sigmas[i]), rel=1e-5)
+            assert fin.in_scale == pytest.approx(1.0 / (sigma_s ** 2 + 1) ** 0.5, rel=1e-5)
