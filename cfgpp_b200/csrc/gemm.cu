@@ -15,6 +15,13 @@
 #include "common.cuh"
 #include "gemm.cuh"
 
+#ifdef CFGPP_DIAG_NOTMA  // diagnostic build: operand (and residual) loads disappear; use on ops without a residual
+#define tma_load_2d(...) ((void)0)
+#define tma_load_4d(...) ((void)0)
+#define tma_load_2d_cg2(...) ((void)0)
+#define tma_load_4d_cg2(...) ((void)0)
+#endif
+
 namespace cfgpp {
 
 void gemm_configure();
@@ -141,8 +148,8 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
   const int num_mg = (p.num_m_blocks + CL - 1) / CL;
   const int num_tiles = num_mg * p.num_n_blocks;
   const int nkb = p.num_k_blocks;
-  auto tile_m_blk = [&](int tile) { return (tile % num_mg) * CL + cta_rank; };
-  auto tile_n_blk = [&](int tile) { return tile / num_mg; };
+  auto tile_m_blk = [&](int tile) { return (p.raster ? tile / p.num_n_blocks : tile % num_mg) * CL + cta_rank; };
+  auto tile_n_blk = [&](int tile) { return p.raster ? tile % p.num_n_blocks : tile / num_mg; };
 
   // ---- work schedule: "stream-K for the remainder" -------------------------------------------------------------
   // D = the tiles that fill whole rounds over the clusters are walked data-parallel (tile = cluster + r * clusters);
@@ -254,8 +261,18 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
             // non-elected lanes only keep the loop state in step
           } else if constexpr (CL == 1) {
             if (item_i == 0 && kb == item.kb0) TL(3);
-            mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-            if (p.conv) {
+#ifdef CFGPP_DIAG_HALFA  // diagnostic build: A arrives on even k-blocks only (the ingest of a tile twice as wide)
+            const bool load_a = !(kb & 1);
+#else
+            const bool load_a = true;
+#endif
+#ifdef CFGPP_DIAG_NOTMA  // diagnostic build (tools/build_variant.sh): no operand traffic, the MMAs run on stale smem
+            mbar_arrive(&full_bar[stage]);
+#else
+            mbar_arrive_expect_tx(&full_bar[stage], load_a ? C::STAGE_BYTES : C::B_BYTES);
+#endif
+            if (!load_a) {
+            } else if (p.conv) {
               const int tap = kb / p.cpb;
               const int cb = kb - tap * p.cpb;
               const int kh = tap / 3, kw = tap - kh * 3;
@@ -272,8 +289,18 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
           } else {
             if (item_i == 0 && kb == item.kb0) TL(3);
             // both CTAs fill their own smem; all bytes are accounted on the leader's barrier (the MMA issuer's)
-            if (is_leader_cta) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
-            if (p.conv) {
+#ifdef CFGPP_DIAG_HALFA
+            const bool load_a = !(kb & 1);
+#else
+            const bool load_a = true;
+#endif
+#ifdef CFGPP_DIAG_NOTMA
+            if (is_leader_cta) mbar_arrive(&full_bar[stage]);
+#else
+            if (is_leader_cta) mbar_arrive_expect_tx(&full_bar[stage], 2 * (load_a ? C::STAGE_BYTES : C::B_BYTES));
+#endif
+            if (!load_a) {
+            } else if (p.conv) {
               const int tap = kb / p.cpb;
               const int cb = kb - tap * p.cpb;
               const int kh = tap / 3, kw = tap - kh * 3;
@@ -322,6 +349,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
             if (it == 0 && kb == kb_first) TL(4);
             if (it == 0 && kb == kb_last) TL(5);
             if (kb == kb_last) TL(6);
+#ifndef CFGPP_DIAG_NOMMA  // diagnostic build: operand traffic only, the commits below retire at once
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
@@ -330,6 +358,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
               else
                 umma_f16_cg2(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (preloaded || kb != kb_first || k != 0) ? 1u : 0u);
             }
+#endif
             // on retirement: free the smem slot (pair: in both CTAs) and, after the last k-block, publish the
             // accumulator
             if constexpr (CL == 1) {
@@ -787,6 +816,18 @@ double streamk_min_saved() {  // k-blocks of main loop the split must save per c
   }
   return v;
 }
+// Tile walk of the linear layers: N-fastest, so the clusters running concurrently cover few M groups and every A tile is
+// fetched from HBM once (the activations of the 64 x 64 / 128 x 128 levels — 84 MB at M = 16384, K = 2560 — do not
+// survive num_n_blocks M-fastest passes in the 126 MB L2: 61.8 -> 54.4 us there, 61.2 -> 51.3 us at M = 65536, N = 320;
+// neutral elsewhere, same box). CFGPP_RASTER=0 restores the M-fastest walk; the convolutions keep it (no difference).
+int raster_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CFGPP_RASTER");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
 bool streamk_linear() {
   static int v = -1;
   if (v < 0) {
@@ -861,6 +902,7 @@ void finish_op(GemmOp& op, const __half* w, int force_bn) {
   if (p.geglu) CFGPP_REQUIRE(op.bn == 256 && p.N % 256 == 0, "GEGLU needs N % 256 == 0");
   p.num_m_blocks = (p.M + BM - 1) / BM;
   p.num_n_blocks = (p.N + op.bn - 1) / op.bn;
+  p.raster = p.conv ? 0 : raster_mode();
   op.cluster = (p.num_m_blocks >= 2 && !cluster_disabled()) ? 2 : 1;
   op.map_b = make_tmap_2d(w, p.N, p.K, p.K, op.bn / op.cluster);
   const int n_out = p.geglu ? p.N / 2 : p.N;

@@ -28,6 +28,7 @@ struct GemmParams {
   int H, W;     // conv: OUTPUT spatial size
   int conv_stride;  // conv: 1, or 2 (Downsample2D: the A tile is fetched through a tensor map with element strides 2)
   int k_split;  // linear: first K index served by the second A map (== K when single-source)
+  int raster;   // tile walk: 0 = M-fastest (tile = n * m_groups + m), 1 = N-fastest (tile = m * n_blocks + n)
   const __half* bias;
   const __half* addend;
   int ld_add;

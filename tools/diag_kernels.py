@@ -10,6 +10,7 @@ import time
 import traceback
 from pathlib import Path
 
+import os
 import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
@@ -305,7 +306,7 @@ def bench_gemm_graph():
                              (65536, 320, 960, False)]:
         a = torch.randn(M, K, generator=g).half().to(dev)
         w = (torch.randn(N, K, generator=g) * K ** -0.5).half().to(dev)
-        res = None if geglu else torch.randn(M, N, generator=g).half().to(dev)
+        res = None if (geglu or os.environ.get('DIAG_NO_RES')) else torch.randn(M, N, generator=g).half().to(dev)
         bias = torch.randn(N, generator=g).half().to(dev)
         us = graph_time_us(lambda: nv.op_linear(a, w, bias, res, 1, geglu=geglu))
         print(f"gemm M={M} N={N} K={K} geglu={int(geglu)}: {us:7.1f} us  {2.0 * M * N * K / us / 1e6:6.0f} TFLOP/s", flush=True)
