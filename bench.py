@@ -495,6 +495,33 @@ def run_ours(args, wl):
     except Exception as e:  # noqa: BLE001 — never lose the measured line to an optional leg
         line["vae_decode"] = {"error": repr(e)[:200]}
 
+    # ---- prompt conditioning of one batch (outside the metric; the step before the path) -----------------
+    try:
+        from cfgpp_b200.text_encoder import ClipConditioner
+        towers = [t for t in (getattr(solver, "text_enc_1", None), getattr(solver, "text_enc_2", None),
+                              getattr(solver, "text_encoder", None)) if isinstance(t, ClipConditioner)]
+        if towers:
+            prompts = [""] + [f"a photo of an astronaut riding horse number {i} on mars" for i in range(BATCH)]
+
+            def encode_all():
+                return [t.encode_batch(prompts) for t in towers]
+            encode_all()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                encode_all()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            fl = sum(t.encoder.stats["flops"] for t in towers)
+            line["text_encode"] = {"ms_per_batch": ms, "prompts": len(prompts), "towers": [t.encoder.cfg.name for t in towers],
+                                   "tflops": fl / (ms / 1e3) / 1e12, "share_of_trajectory": ms / (ms_dev / args.steps),
+                                   "what": "native CLIP text towers (cfgpp_clip_encode) incl. host tokenisation, "
+                                           "device-timed, not part of `value`"}
+    except Exception as e:  # noqa: BLE001
+        line["text_encode"] = {"error": repr(e)[:200]}
+
     def checkpoint_line():
         s = json.dumps(line)
         print("[bench partial] " + s, file=sys.stderr, flush=True)
