@@ -89,14 +89,15 @@ def op_conv3x3(x_nhwc: torch.Tensor, w_packed: torch.Tensor, bias=None, addend=N
     return out
 
 
-def op_conv3x3_s2(x_nhwc: torch.Tensor, w_packed: torch.Tensor, bias=None) -> torch.Tensor:
-    """Downsample2D conv: x [B,H,W,Cin] fp16 NHWC (even H, W), w_packed [Cout, 9*Cin] (tap-major) -> [B,H/2,W/2,Cout]."""
+def op_conv3x3_s2(x_nhwc: torch.Tensor, w_packed: torch.Tensor, bias=None, pad: int = 1) -> torch.Tensor:
+    """Downsample2D conv: x [B,H,W,Cin] fp16 NHWC (even H, W), w_packed [Cout, 9*Cin] (tap-major) -> [B,H/2,W/2,Cout].
+    pad=1: symmetric zero padding (UNet); pad=0: one zero row / column after the image (AutoencoderKL encoder)."""
     lib = load()
     B, H, W, Cin = x_nhwc.shape
     Cout = w_packed.shape[0]
     out = torch.empty((B, H // 2, W // 2, Cout), dtype=torch.float16, device=x_nhwc.device)
     check(lib.cfgpp_op_conv3x3_s2(ptr(x_nhwc), c_int(B), c_int(H), c_int(W), c_int(Cin), ptr(w_packed), c_int(Cout),
-                                  ptr(bias), ptr(out), stream_ptr()))
+                                  ptr(bias), c_int(pad), ptr(out), stream_ptr()))
     return out
 
 

@@ -52,10 +52,10 @@ CFGPP_API int cfgpp_op_conv3x3(const void* x, int B, int H, int W, int Cin, cons
 }
 
 CFGPP_API int cfgpp_op_conv3x3_s2(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias,
-                                  void* out, void* stream) {
+                                  int pad, void* out, void* stream) {
   return guarded([&] {
     GemmOp op = make_conv3x3_op((const __half*)x, B, H, W, Cin, (const __half*)w, Cout, (const __half*)bias, nullptr, 0, 1,
-                                (__half*)out, 0, 2);
+                                (__half*)out, 0, 2, pad);
     run_gemm_op(op, (cudaStream_t)stream);
   });
 }

@@ -36,6 +36,13 @@ CFGPP_API int cfgpp_vae_decode(cfgpp_vae_handle* h, const void* z, int z_dtype, 
   return guarded([&] { h->vae.decode(z, z_dtype, batch, h_lat, w_lat, (__half*)image, (cudaStream_t)stream); });
 }
 
+CFGPP_API int cfgpp_vae_encode(cfgpp_vae_handle* h, const void* image, int image_dtype, int batch, int height, int width,
+                               const void* noise, void* latent, void* stream) {
+  return guarded([&] {
+    h->vae.encode(image, image_dtype, batch, height, width, (const __half*)noise, (float*)latent, (cudaStream_t)stream);
+  });
+}
+
 CFGPP_API int cfgpp_vae_stats(cfgpp_vae_handle* h, double* flops, size_t* workspace_bytes) {
   return guarded([&] {
     if (flops) *flops = h->vae.flops();

@@ -276,7 +276,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
               const int tap = kb / p.cpb;
               const int cb = kb - tap * p.cpb;
               const int kh = tap / 3, kw = tap - kh * 3;
-              tma_load_4d(sa, &map_a, &full_bar[stage], cb * BK, w0 * p.conv_stride + kw - 1, h0 * p.conv_stride + kh - 1,
+              tma_load_4d(sa, &map_a, &full_bar[stage], cb * BK, w0 * p.conv_stride + kw - p.conv_pad, h0 * p.conv_stride + kh - p.conv_pad,
                           img);
             } else {
               const int k0 = kb * BK;
@@ -304,8 +304,8 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap map_a, const
               const int tap = kb / p.cpb;
               const int cb = kb - tap * p.cpb;
               const int kh = tap / 3, kw = tap - kh * 3;
-              tma_load_4d_cg2(sa, &map_a, &full_bar[stage], cb * BK, w0 * p.conv_stride + kw - 1,
-                              h0 * p.conv_stride + kh - 1, img);
+              tma_load_4d_cg2(sa, &map_a, &full_bar[stage], cb * BK, w0 * p.conv_stride + kw - p.conv_pad,
+                              h0 * p.conv_stride + kh - p.conv_pad, img);
             } else {
               const int k0 = kb * BK;
               if (k0 < p.k_split)
@@ -986,7 +986,7 @@ GemmOp make_linear_op(const __half* a, int lda, const __half* a2, int lda2, int 
   CFGPP_REQUIRE(N % 8 == 0 && ldc % 8 == 0, "N and ldc must be multiples of 8");
   p.M = M; p.N = N; p.K = K;
   p.num_k_blocks = K / BK;
-  p.conv = 0; p.cpb = 1; p.H = p.W = 1;
+  p.conv = 0; p.cpb = 1; p.H = p.W = 1; p.conv_pad = 1;
   p.k_split = a2 ? k_split : K;
   if (a2) CFGPP_REQUIRE(k_split % BK == 0 && k_split > 0 && k_split < K, "k_split must be a multiple of 64");
   p.bias = bias; p.addend = addend; p.ld_add = ld_add;
@@ -999,10 +999,12 @@ GemmOp make_linear_op(const __half* a, int lda, const __half* a2, int lda2, int 
 }
 
 GemmOp make_conv3x3_op(const __half* x, int B, int H, int W, int Cin, const __half* w, int Cout, const __half* bias,
-                       const __half* addend, int ld_add, int add_rows_per_group, __half* out, int force_bn, int stride) {
+                       const __half* addend, int ld_add, int add_rows_per_group, __half* out, int force_bn, int stride,
+                       int pad) {
   GemmOp op{};
   GemmParams& p = op.p;
   CFGPP_REQUIRE(stride == 1 || stride == 2, "conv3x3 stride must be 1 or 2");
+  CFGPP_REQUIRE(pad == 1 || (pad == 0 && stride == 2), "conv3x3 pad: 1, or 0 with stride 2 (zero row / column after the image)");
   CFGPP_REQUIRE(Cin % BK == 0, "conv3x3 Cin must be a multiple of 64");
   CFGPP_REQUIRE(Cout % 8 == 0, "conv3x3 Cout must be a multiple of 8");
   CFGPP_REQUIRE(stride == 1 || (H % 2 == 0 && W % 2 == 0), "stride-2 conv3x3 needs even H, W");
@@ -1014,12 +1016,12 @@ GemmOp make_conv3x3_op(const __half* x, int B, int H, int W, int Cin, const __ha
   const int Nt = BM / (Wt * Ht);
   p.M = B * Ho * Wo; p.N = Cout; p.K = 9 * Cin;
   p.num_k_blocks = 9 * (Cin / BK);
-  p.conv = 1; p.cpb = Cin / BK; p.H = Ho; p.W = Wo; p.conv_stride = stride;
+  p.conv = 1; p.cpb = Cin / BK; p.H = Ho; p.W = Wo; p.conv_stride = stride; p.conv_pad = pad;
   p.k_split = p.K;
   p.bias = bias; p.addend = addend; p.ld_add = ld_add;
   p.add_rows_per_group = add_rows_per_group < 1 ? 1 : add_rows_per_group;
   p.out = out; p.ldc = Cout; p.geglu = 0;
-  // the A tile of tap (kh, kw): output pixel (y, x) reads input pixel (stride * y + kh - 1, stride * x + kw - 1); the
+  // the A tile of tap (kh, kw): output pixel (y, x) reads input pixel (stride * y + kh - pad, stride * x + kw - pad); the
   // box spans stride * extent input pixels and the tensor map's element strides pick every stride-th one
   uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
   uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};

@@ -27,6 +27,8 @@ struct GemmParams {
   int cpb;      // conv: channel blocks (Cin / 64) per tap
   int H, W;     // conv: OUTPUT spatial size
   int conv_stride;  // conv: 1, or 2 (Downsample2D: the A tile is fetched through a tensor map with element strides 2)
+  int conv_pad;     // conv: 1 (symmetric zero padding), or 0 with stride 2 (the VAE encoder's Downsample2D pads one zero
+                    // row / column AFTER the image: taps at 2y + kh, out-of-image reads are the TMA's zero fill)
   int k_split;  // linear: first K index served by the second A map (== K when single-source)
   int raster;   // tile walk: 0 = M-fastest (tile = n * m_groups + m), 1 = N-fastest (tile = m * n_blocks + n)
   const __half* bias;
@@ -69,10 +71,11 @@ GemmOp make_linear_op(const __half* a, int lda, const __half* a2, int lda2, int 
                       __half* out, int ldc, bool geglu, int force_bn = 0);
 
 // Conv3x3 stride 1 pad 1 on NHWC input x [B,H,W,Cin], weight [Cout][9][Cin], out NHWC [B,H,W,Cout].
-// stride 2 (pad 1): x is [B,H,W,Cin] with even H, W; out is [B,H/2,W/2,Cout].
+// stride 2: x is [B,H,W,Cin] with even H, W; out is [B,H/2,W/2,Cout]; pad 1 (UNet Downsample2D) or pad 0 (the
+// AutoencoderKL encoder's: F.pad(x, (0, 1, 0, 1)) followed by an un-padded stride-2 convolution).
 GemmOp make_conv3x3_op(const __half* x, int B, int H, int W, int Cin, const __half* w, int Cout,
                        const __half* bias, const __half* addend, int ld_add, int add_rows_per_group, __half* out,
-                       int force_bn = 0, int stride = 1);
+                       int force_bn = 0, int stride = 1, int pad = 1);
 
 void run_gemm_op(const GemmOp& op, cudaStream_t stream);
 

@@ -27,6 +27,10 @@ void run_vae_latent_prep(const void* z, int z_is_half, float scaling, const __ha
 void run_vae_row_softmax(__half* s, int rows, int n, float scale_log2e, cudaStream_t stream);
 void run_vae_conv_rgb(const __half* x, const __half* w, const __half* bias, __half* out, int B, int H, int W, int C,
                       cudaStream_t stream);
+void run_vae_image_pad(const void* x, int x_is_half, __half* out, int B, int H, int W, cudaStream_t stream);
+void run_vae_moments_sample(const __half* x, const __half* w, const __half* bias, const __half* wq, const __half* bq,
+                            const __half* noise, float scaling, float* out, int B, int H, int W, int C,
+                            cudaStream_t stream);
 
 class VaeDecoder {
  public:
@@ -37,6 +41,13 @@ class VaeDecoder {
   void finalize_weights(cudaStream_t stream);
   // z: (batch, 4, h, w) NCHW of z_dtype (the scaled latent zt); image: (batch, 3, 8h.., 8w..) NCHW fp16
   void decode(const void* z, int z_dtype, int batch, int h_lat, int w_lat, __half* image, cudaStream_t stream);
+  // ENCODER half (`vae.encode(x).latent_dist.sample() * scaling_factor`, latent_sdxl.py:151-152, latent_diffusion.py:
+  // 117-121; weights `encoder.*`, `quant_conv.*`): image (batch,3,H,W) NCHW of x_dtype -> scaled latent (batch,4,H/8,W/8)
+  // fp32 (what the fp16 module returns under the reference's autocast). noise: the caller's `randn(mean.shape)` draw in fp16, or null for the posterior mean.
+  void encode(const void* image, int x_dtype, int batch, int H, int W, const __half* noise, float* latent,
+              cudaStream_t stream);
+  bool has_encoder() const { return raw_.count("encoder.conv_in.weight") != 0; }
+  double encode_flops() const { return enc_flops_; }
   double flops() const { return flops_; }
   size_t workspace_bytes() const { return workspace_bytes_; }
 
@@ -56,11 +67,13 @@ class VaeDecoder {
   void* alloc_bytes(size_t bytes);
   __half* alloc_act(size_t numel) { return static_cast<__half*>(alloc_bytes(numel * sizeof(__half))); }
   void prepare(int batch, int h_lat, int w_lat);
-  void add(std::function<void(cudaStream_t)> fn) { plan_.push_back(std::move(fn)); }
+  void prepare_encode(int batch, int H, int W);
+  void add(std::function<void(cudaStream_t)> fn) { cur_plan_->push_back(std::move(fn)); }
   void add_gemm(const GemmOp& op) {
-    flops_ += op.flops();
-    plan_.push_back([op](cudaStream_t st) { run_gemm_op(op, st); });
+    *cur_flops_ += op.flops();
+    cur_plan_->push_back([op](cudaStream_t st) { run_gemm_op(op, st); });
   }
+  void alloc_scratch(size_t max_act, size_t ntok, int Ct);  // the builders' scratch set, into the current allocation list
   // builders return the output activation pointer
   __half* build_resnet(const std::string& prefix, const __half* x, int Cin, int Cout, int H, int W);
   __half* build_attention(const std::string& prefix, const __half* x, int C, int H, int W);
@@ -72,12 +85,24 @@ class VaeDecoder {
   std::map<std::string, Tensor> raw_;
   std::map<std::string, __half*> packed_;
   std::vector<void*> weight_allocs_;
-  std::vector<void*> act_allocs_;
+  std::vector<void*> act_allocs_;   // decode plan
+  std::vector<void*> enc_allocs_;   // encode plan
+  std::vector<void*>* cur_allocs_ = &act_allocs_;
   size_t workspace_bytes_ = 0;
   double flops_ = 0.0;
   // plan for the prepared (batch, h, w)
   int B_ = 0, H_ = 0, W_ = 0;
-  std::vector<std::function<void(cudaStream_t)>> plan_;
+  std::vector<std::function<void(cudaStream_t)>> plan_, enc_plan_;
+  std::vector<std::function<void(cudaStream_t)>>* cur_plan_ = &plan_;
+  double enc_flops_ = 0.0;
+  double* cur_flops_ = &flops_;
+  int nb_ = 0;                     // batch the builders lay the current plan out for
+  int eB_ = 0, eH_ = 0, eW_ = 0;   // prepared encode shape
+  const void* x_in_ = nullptr;     // set per encode() call
+  int x_is_half_ = 0;
+  const __half* noise_in_ = nullptr;
+  float* latent_out_ = nullptr;
+  __half* conv_in_w4_ = nullptr;   // encoder.conv_in.weight (C,3,3,3) zero-padded to (C,4,3,3)
   const void* z_in_ = nullptr;   // set per decode() call (read by the first plan step through these members)
   int z_is_half_ = 0;
   __half* image_out_ = nullptr;

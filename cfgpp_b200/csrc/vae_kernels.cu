@@ -9,6 +9,8 @@ namespace cfgpp {
 
 namespace {
 
+CFGPP_DEVICE float rh(float x) { return __half2float(__float2half_rn(x)); }  // round through fp16
+
 // z (B,4,H,W) fp32 / fp16 -> fp16( Wpq . fp16(z / s) + b )  (B,4,H,W) fp16.
 // Reference: `self.vae.decode(zt / scaling_factor)` under autocast (latent_sdxl.py:163): the division happens in zt's
 // dtype, post_quant_conv (fp16 weights) casts its input to fp16 and rounds its output to fp16.
@@ -147,6 +149,95 @@ __global__ void __launch_bounds__(128) vae_conv_rgb_kernel(const __half* __restr
     out[(static_cast<size_t>(b) * 3 + o) * HW + r] = __float2half_rn(acc[o] + __half2float(bias[o]));
 }
 
+// Image (B,3,H,W) NCHW fp16 / fp32 -> (B,4,H,W) fp16 with a zero fourth plane: the encoder's conv_in (3 -> C) then runs
+// on the UNet's conv_in kernel (4 input channels) with a zero-padded weight.
+__global__ void vae_image_pad_kernel(const void* __restrict__ x, int x_is_half, __half* __restrict__ out, int B, size_t HW) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t total = static_cast<size_t>(B) * 4 * HW;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t plane = i / HW;
+    const int c = static_cast<int>(plane & 3);
+    const size_t b = plane >> 2;
+    __half v = __float2half(0.f);
+    if (c < 3) {
+      const size_t src = (b * 3 + c) * HW + (i - plane * HW);
+      v = x_is_half ? reinterpret_cast<const __half*>(x)[src] : __float2half_rn(reinterpret_cast<const float*>(x)[src]);
+    }
+    out[i] = v;
+  }
+}
+
+// Encoder tail: conv_out (3x3 pad 1, C -> 8 moments) on the GroupNorm+SiLU'ed NHWC input, quant_conv (1x1, 8 -> 8),
+// DiagonalGaussianDistribution (mean | logvar, logvar clamped to [-30, 20], std = exp(logvar / 2)) and
+// `latent_dist.sample() * scaling_factor` with the caller's noise draw. One warp per latent pixel. Rounding points of the
+// fp16 module under the reference's torch.autocast (every `sample()` runs inside one): conv_out and quant_conv outputs
+// and 0.5 * logvar are fp16; `exp` is on autocast's fp32 list, so std, std * noise, + mean and * scaling_factor are
+// fp32 and the latent leaves as fp32.
+__global__ void __launch_bounds__(256) vae_moments_sample_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
+                                                                 const __half* __restrict__ bias,
+                                                                 const __half* __restrict__ wq,
+                                                                 const __half* __restrict__ bq,
+                                                                 const __half* __restrict__ noise, float scaling,
+                                                                 float* __restrict__ out, int B, int H, int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ __half swm[];  // [8][9][C]
+  for (int i = threadIdx.x * 8; i < 72 * C; i += blockDim.x * 8)
+    *reinterpret_cast<uint4*>(swm + i) = *reinterpret_cast<const uint4*>(w + i);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HW = H * W;
+  const int pix = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (pix >= B * HW) return;
+  const int b = pix / HW, r = pix - b * HW;
+  const int h = r / W, xw = r - h * W;
+  const int vpt = C >> 3;
+  float acc[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+  for (int v = lane; v < 9 * vpt; v += 32) {
+    const int tap = v / vpt;
+    const int c0 = (v - tap * vpt) * 8;
+    const int hh = h + tap / 3 - 1, ww = xw + tap % 3 - 1;
+    if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+    const uint4 ux = *reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(b) * H + hh) * W + ww) * C + c0);
+    const __half2* hx = reinterpret_cast<const __half2*>(&ux);
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const uint4 uw = *reinterpret_cast<const uint4*>(swm + (o * 9 + tap) * C + c0);
+      const __half2* hw = reinterpret_cast<const __half2*>(&uw);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 a = __half22float2(hx[i]), wf = __half22float2(hw[i]);
+        acc[o] += a.x * wf.x + a.y * wf.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 8; ++o)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], d);
+  if (lane < 4) {
+    float m[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) m[o] = rh(acc[o] + __half2float(bias[o]));
+    float q_mean = __half2float(bq[lane]), q_logvar = __half2float(bq[4 + lane]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      q_mean += __half2float(wq[lane * 8 + i]) * m[i];
+      q_logvar += __half2float(wq[(4 + lane) * 8 + i]) * m[i];
+    }
+    const float mean = rh(q_mean);
+    const float logvar = fminf(fmaxf(rh(q_logvar), -30.f), 20.f);
+    const float stdv = expf(rh(0.5f * logvar));
+    const size_t i = (static_cast<size_t>(b) * 4 + lane) * HW + r;
+    const float nz = noise ? __half2float(noise[i]) : 0.f;
+    out[i] = __fmul_rn(__fadd_rn(mean, __fmul_rn(stdv, nz)), scaling);
+  }
+}
+
 }  // namespace
 
 void run_vae_latent_prep(const void* z, int z_is_half, float scaling, const __half* w, const __half* bias, __half* out,
@@ -167,6 +258,33 @@ void run_vae_conv_rgb(const __half* x, const __half* w, const __half* bias, __ha
   const size_t total = static_cast<size_t>(B) * H * W;
   launch_pdl(vae_conv_rgb_kernel, dim3(static_cast<unsigned>((total + 127) / 128)), dim3(128),
              static_cast<size_t>(27) * C * sizeof(__half), stream, x, w, bias, out, B, H, W, C);
+}
+
+}  // namespace cfgpp
+
+namespace cfgpp {
+
+void run_vae_image_pad(const void* x, int x_is_half, __half* out, int B, int H, int W, cudaStream_t stream) {
+  const size_t HW = static_cast<size_t>(H) * W;
+  const size_t total = static_cast<size_t>(B) * 4 * HW;
+  const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 32));
+  launch_pdl(vae_image_pad_kernel, dim3(blocks), dim3(256), 0, stream, x, x_is_half, out, B, HW);
+}
+
+void run_vae_moments_sample(const __half* x, const __half* w, const __half* bias, const __half* wq, const __half* bq,
+                            const __half* noise, float scaling, float* out, int B, int H, int W, int C,
+                            cudaStream_t stream) {
+  const size_t smem = static_cast<size_t>(72) * C * sizeof(__half);
+  CFGPP_REQUIRE(C % 8 == 0 && smem <= 160 * 1024, "encoder conv_out: C % 8 == 0 and weights within 160 KB of shared memory");
+  static bool configured = false;
+  if (!configured) {
+    CFGPP_CHECK_CUDA(cudaFuncSetAttribute(vae_moments_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    configured = true;
+  }
+  const int warps = 8;
+  const int total = B * H * W;
+  launch_pdl(vae_moments_sample_kernel, dim3((total + warps - 1) / warps), dim3(warps * 32), smem, stream, x, w, bias, wq, bq,
+             noise, scaling, out, B, H, W, C);
 }
 
 }  // namespace cfgpp

@@ -170,6 +170,14 @@ int cfgpp_vae_finalize_weights(cfgpp_vae_handle* h, void* stream);
  * The plan / workspace for (batch,h,w) is built on first use and cached. */
 int cfgpp_vae_decode(cfgpp_vae_handle* h, const void* zt_dev, int z_dtype, int batch, int h_lat, int w_lat,
                      void* image_dev, void* stream);
+/* ENCODER half — replaces `self.vae.encode(x).latent_dist.sample() * scaling_factor` (latent_sdxl.py:151-152,
+ * latent_diffusion.py:117-121), the front end of the inversion / editing solvers. Needs the `encoder.*` and
+ * `quant_conv.*` weights to have been loaded. image_dev: (batch,3,H,W) NCHW of image_dtype in [-1, 1];
+ * noise_dev: (batch,4,H/8,W/8) fp16 — the `randn` draw of DiagonalGaussianDistribution.sample, made by the caller —
+ * or NULL for the posterior mean; latent_out: (batch,4,H/8,W/8) fp32 (the fp16 module's output under the reference's
+ * autocast: `exp` promotes the posterior's std to fp32), already multiplied by scaling_factor. */
+int cfgpp_vae_encode(cfgpp_vae_handle* h, const void* image_dev, int image_dtype, int batch, int height, int width,
+                     const void* noise_dev, void* latent_out, void* stream);
 /* Algorithmic FLOPs of one decode of the prepared shape, and its activation workspace. */
 int cfgpp_vae_stats(cfgpp_vae_handle* h, double* flops, size_t* workspace_bytes);
 
@@ -210,10 +218,11 @@ int cfgpp_op_linear(const void* a, int lda, const void* a2, int lda2, int k_spli
                     int geglu, int force_bn, void* stream);
 int cfgpp_op_conv3x3(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias,
                      const void* addend, int ld_add, int add_rows_per_group, void* out, int force_bn, void* stream);
-/* Downsample2D: 3x3, stride 2, pad 1 on NHWC x [B,H,W,Cin] (even H, W) -> [B,H/2,W/2,Cout]; the A tile is fetched by TMA
- * with element strides 2 (no im2col copy). */
-int cfgpp_op_conv3x3_s2(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias, void* out,
-                        void* stream);
+/* Downsample2D: 3x3, stride 2 on NHWC x [B,H,W,Cin] (even H, W) -> [B,H/2,W/2,Cout]; the A tile is fetched by TMA with
+ * element strides 2 (no im2col copy). pad = 1: the UNet's (symmetric zero padding); pad = 0: the AutoencoderKL encoder's
+ * (one zero row / column AFTER the image, F.pad(x, (0, 1, 0, 1)) + un-padded convolution). */
+int cfgpp_op_conv3x3_s2(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias, int pad,
+                        void* out, void* stream);
 /* head h of q / k / v / out occupies columns [h*P, h*P + head_dim) with P = head_dim rounded up to a multiple of 64
  * (columns head_dim..P-1 must be zero in q / k / v and come back zero in out). */
 int cfgpp_op_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B,

@@ -1,6 +1,8 @@
-"""ORACLE (test infrastructure, not product code): pure-PyTorch restatement of the DECODER half of diffusers 0.27.1
-`AutoencoderKL` — the model behind `self.vae.decode(zt / scaling_factor).sample` (reference latent_sdxl.py:155-164,
-VAE = madebyollin/sdxl-vae-fp16-fix :44; latent_diffusion.py:123-129, VAE of runwayml/stable-diffusion-v1-5 :64).
+"""ORACLE (test infrastructure, not product code): pure-PyTorch restatement of diffusers 0.27.1 `AutoencoderKL` — the
+DECODER behind `self.vae.decode(zt / scaling_factor).sample` (reference latent_sdxl.py:155-164, VAE =
+madebyollin/sdxl-vae-fp16-fix :44; latent_diffusion.py:123-129, VAE of runwayml/stable-diffusion-v1-5 :64) and the
+ENCODER + posterior behind `self.vae.encode(x).latent_dist.sample() * scaling_factor` (latent_sdxl.py:151-152,
+latent_diffusion.py:117-121; keys `encoder.*`, `quant_conv.*`).
 
 PARITY UNPINNED against the real library: diffusers is not installable offline and the reference ships no golden
 vectors. Module names equal the diffusers state-dict keys (`post_quant_conv`, `decoder.conv_in`,
@@ -151,6 +153,89 @@ class AutoencoderKLDecoder(nn.Module):
 
     def forward(self, z):
         return self.decoder(self.post_quant_conv(z))
+
+
+class VaeDownsample(nn.Module):
+    """Downsample2D(use_conv=True, padding=0): zero-pad right / bottom by one pixel, then a stride-2 3x3 convolution."""
+    def __init__(self, c: int):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, stride=2, padding=0)
+
+    def forward(self, x):
+        return self.conv(F.pad(x, (0, 1, 0, 1), mode="constant", value=0))
+
+
+class VaeDownBlock(nn.Module):
+    """DownEncoderBlock2D: `layers` resnets, then the downsampler (all but the last block)."""
+    def __init__(self, cin: int, cout: int, layers: int, groups: int, add_downsample: bool):
+        super().__init__()
+        self.resnets = nn.ModuleList([VaeResnetBlock2D(cin if i == 0 else cout, cout, groups) for i in range(layers)])
+        self.downsamplers = nn.ModuleList([VaeDownsample(cout)]) if add_downsample else None
+
+    def forward(self, x):
+        for r in self.resnets:
+            x = r(x)
+        if self.downsamplers is not None:
+            x = self.downsamplers[0](x)
+        return x
+
+
+class Encoder(nn.Module):
+    """diffusers 0.27.1 `Encoder` (double_z=True): conv_in -> down_blocks -> mid_block -> GroupNorm + SiLU -> conv_out
+    (2 * latent_channels moments)."""
+    def __init__(self, cfg: VAEConfig):
+        super().__init__()
+        boc, g = cfg.block_out_channels, cfg.norm_num_groups
+        self.conv_in = nn.Conv2d(cfg.out_channels, boc[0], 3, padding=1)
+        downs, cout = [], boc[0]
+        for i, c in enumerate(boc):
+            cin, cout = cout, c
+            downs.append(VaeDownBlock(cin, cout, cfg.layers_per_block, g, add_downsample=(i != len(boc) - 1)))
+        self.down_blocks = nn.ModuleList(downs)
+        self.mid_block = VaeMidBlock(boc[-1], g)
+        self.conv_norm_out = nn.GroupNorm(g, boc[-1], eps=1e-6)
+        self.conv_out = nn.Conv2d(boc[-1], 2 * cfg.latent_channels, 3, padding=1)
+
+    def forward(self, x):
+        x = self.conv_in(x)
+        for blk in self.down_blocks:
+            x = blk(x)
+        x = self.mid_block(x)
+        return self.conv_out(F.silu(self.conv_norm_out(x)))
+
+
+class AutoencoderKLEncoder(nn.Module):
+    """`AutoencoderKL.encode(x).latent_dist`: encoder, quant_conv (1x1), DiagonalGaussianDistribution. `forward`
+    returns (mean, std) with the distribution's clamp of the log-variance to [-30, 20]."""
+    def __init__(self, cfg: VAEConfig):
+        super().__init__()
+        self.cfg = cfg
+        self.encoder = Encoder(cfg)
+        self.quant_conv = nn.Conv2d(2 * cfg.latent_channels, 2 * cfg.latent_channels, 1)
+
+    def forward(self, x):
+        moments = self.quant_conv(self.encoder(x))
+        mean, logvar = torch.chunk(moments, 2, dim=1)
+        logvar = torch.clamp(logvar, -30.0, 20.0)
+        return mean, torch.exp(0.5 * logvar)
+
+
+def build_vae_encoder(cfg: VAEConfig, state_dict=None, dtype=torch.float32, device="cpu") -> AutoencoderKLEncoder:
+    if state_dict is None:
+        return AutoencoderKLEncoder(cfg).to(device=device, dtype=dtype).eval().requires_grad_(False)
+    with torch.device("meta"):
+        m = AutoencoderKLEncoder(cfg)
+    m.load_state_dict({k: v.to(device=device, dtype=dtype) for k, v in state_dict.items()}, strict=True, assign=True)
+    return m.eval().requires_grad_(False)
+
+
+@torch.no_grad()
+def encode(vae: AutoencoderKLEncoder, x: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
+    """SDXL.encode / StableDiffusion.encode: `vae.encode(x).latent_dist.sample() * scaling_factor`
+    (latent_sdxl.py:151-152, latent_diffusion.py:117-121); `noise` is the `randn_tensor(mean.shape, dtype=param dtype)`
+    draw of DiagonalGaussianDistribution.sample, made by the caller so both sides consume the same values."""
+    mean, std = vae(x)
+    return (mean + std * noise.to(mean.dtype)) * vae.cfg.scaling_factor
 
 
 def count_params(m: nn.Module) -> int:

@@ -110,6 +110,21 @@ def test_conv3x3_stride2(B, H, W, Cin, Cout):
     gate(f'conv3x3 stride 2 {B}x{H}x{W} {Cin}->{Cout}', out, ref.permute(0, 2, 3, 1).reshape(-1, Cout), TOL_GEMM)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 256, 256, 128, 128), (2, 128, 128, 256, 256), (2, 32, 32, 64, 64),
+                                            (1, 64, 128, 128, 128)])
+def test_conv3x3_stride2_pad_after(B, H, W, Cin, Cout):
+    """The AutoencoderKL encoder's Downsample2D: F.pad(x, (0, 1, 0, 1)) then an un-padded stride-2 conv — the same
+    stride-2 tensor map started AT the pixel, the zero row / column after the image being the TMA's out-of-bounds fill."""
+    from cfgpp_b200 import _native as nv
+    g = torch.Generator().manual_seed(H + Cin + 1)
+    x, w, bias = rnd(g, B, Cin, H, W), rnd(g, Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5), rnd(g, Cout)
+    out = nv.op_conv3x3_s2(x.permute(0, 2, 3, 1).contiguous(), w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous(),
+                           bias, pad=0).reshape(-1, Cout)
+    ref = torch.nn.functional.conv2d(torch.nn.functional.pad(x.float(), (0, 1, 0, 1)), w.float(), bias.float(), stride=2).half()
+    assert ref.shape[-2:] == (H // 2, W // 2)
+    gate(f'conv3x3 stride 2 pad-after {B}x{H}x{W} {Cin}->{Cout}', out, ref.permute(0, 2, 3, 1).reshape(-1, Cout), TOL_GEMM)
+
+
 def test_conv3x3_streamk_repeatable():
     """The conv shapes of the 1280-channel level take the stream-K split by default: 10 launches, bit-identical."""
     from cfgpp_b200 import _native as nv

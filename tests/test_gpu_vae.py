@@ -121,3 +121,89 @@ def test_native_vae_against_committed_golden():
     print(f"tiny_vae vs golden fp32 image: rel-L2 {e:.3e}")
     assert e <= 5e-3
     dec.close()
+
+
+# ---- encoder half: `vae.encode(x).latent_dist.sample() * scaling_factor` (latent_sdxl.py:151-152, latent_diffusion.py:117-121)
+
+def _enc_case(kind, B, H, W, xdtype=torch.float16, seed=9, check32=True):
+    from cfgpp_b200 import vae as V
+    from oracle import vae as OV
+    cfg = V.VAE_CONFIGS[kind]()
+    sd = V.synthetic_vae_state_dict(cfg, seed=seed, device=dev, with_encoder=True)
+    esd = {k: v for k, v in sd.items() if k.startswith(("encoder.", "quant_conv."))}
+    g = torch.Generator().manual_seed(seed + 1)
+    x = (torch.rand(B, 3, H, W, generator=g) * 2 - 1).to(xdtype).to(dev)
+    noise = torch.randn(B, 4, H // 8, W // 8, generator=g).half().to(dev)
+    vae = V.NativeVAEDecoder(cfg, sd, dev)
+    assert vae.has_encoder
+    z = vae.encode(x, noise)
+    zm = vae.encode(x, sample=False)
+    assert z.dtype == torch.float32 and z.shape == (B, 4, H // 8, W // 8) and torch.isfinite(z).all()
+    assert torch.equal(z, vae.encode(x, noise))  # deterministic, plan reuse
+    # decode still works on the same handle (the two plans own separate workspaces)
+    img = vae.decode(z)
+    assert img.shape == (B, 3, H, W) and torch.isfinite(img).all()
+    assert torch.equal(z, vae.encode(x, noise))
+    vae.close()
+    m16 = OV.build_vae_encoder(_ocfg(cfg), esd, dtype=torch.float16, device=dev)
+    with torch.autocast("cuda", dtype=torch.float16):
+        r16, rm16 = OV.encode(m16, x.half(), noise), OV.encode(m16, x.half(), torch.zeros_like(noise))
+    del m16
+    e16, em16 = rel_l2(z, r16), rel_l2(zm, rm16)
+    msg = f"vae encode {kind} B={B} {H}x{W} x={xdtype}: sample vs fp16 oracle {e16:.3e}, mean {em16:.3e}"
+    if check32:
+        m32 = OV.build_vae_encoder(_ocfg(cfg), esd, dtype=torch.float32, device=dev)
+        r32 = OV.encode(m32, x.float(), noise.float())
+        del m32
+        e32, b32 = rel_l2(z, r32), rel_l2(r16, r32)
+        msg += f", vs fp32 oracle {e32:.3e} (fp16 oracle itself {b32:.3e})"
+        print(msg)
+        assert e32 <= 1.5 * b32 + 1e-4
+    else:
+        print(msg)
+    assert e16 <= 5e-3 and em16 <= 5e-3, msg
+    assert rel_l2(z, zm) > 1e-2   # the noise term is really there
+
+
+@pytest.mark.parametrize("B,H,W,xdtype", [(1, 128, 128, torch.float16), (2, 256, 256, torch.float32), (3, 128, 256, torch.float16)])
+def test_vae_encode_tiny(B, H, W, xdtype):
+    _enc_case("tiny_vae", B, H, W, xdtype)
+
+
+def test_vae_encode_sdxl_512():
+    _enc_case("sdxl_vae", 1, 512, 512)
+
+
+def test_vae_encode_sdxl_full_size():
+    """1024 x 1024, the SDXL editing front end (latent_sdxl.py:288): 1024-wide row-segment tiles, stride-2 convs down to 128 x 128."""
+    _enc_case("sdxl_vae", 1, 1024, 1024, check32=False)
+
+
+def test_solver_encode_uses_native_vae_and_the_callers_rng():
+    """`SDXL.encode` / `StableDiffusion.encode` (the front end of the inversion / editing solvers) on the native encoder;
+    the posterior's noise comes from the CUDA generator exactly as diffusers' randn_tensor draws it."""
+    from types import SimpleNamespace
+    from cfgpp_b200 import latent_sdxl as LX, vae as V
+    from cfgpp_b200.config import tiny_sdxl_config
+    from oracle import vae as OV
+    s = LX.get_solver("ddim_cfg++", solver_config=SimpleNamespace(num_sampling=4), device="cuda:0",
+                      unet_config=tiny_sdxl_config(), model_key="synthetic:7")
+    assert isinstance(s.vae, V.NativeVAE) and s.vae.decoder.has_encoder
+    x = (torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(3)) * 2 - 1).half().to(dev)
+    torch.manual_seed(11)
+    z = s.encode(x)
+    torch.manual_seed(11)
+    noise = torch.randn(1, 4, 32, 32, dtype=torch.float16, device=dev)
+    assert z.shape == (1, 4, 32, 32) and z.dtype == torch.float32
+    cfg = s.vae.decoder.cfg
+    sd = V.synthetic_vae_state_dict(cfg, seed=4242, device=dev, with_encoder=True)
+    m16 = OV.build_vae_encoder(_ocfg(cfg), {k: v for k, v in sd.items() if k.startswith(("encoder.", "quant_conv."))},
+                               dtype=torch.float16, device=dev)
+    with torch.autocast("cuda", dtype=torch.float16):
+        ref = OV.encode(m16, x, noise)
+    e = rel_l2(z, ref)
+    print(f"solver.encode vs oracle with the same generator state: {e:.3e}")
+    assert e <= 5e-3
+    torch.manual_seed(12)
+    assert rel_l2(s.encode(x), z) > 1e-2
+    LX.release_engines()

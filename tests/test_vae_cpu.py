@@ -55,3 +55,33 @@ def test_native_vae_fails_loudly_without_cuda():
     cfg = V.tiny_vae_config()
     with pytest.raises(nv.NativeError, match="CUDA"):
         V.NativeVAEDecoder(cfg, V.synthetic_vae_state_dict(cfg), "cpu")
+
+
+def test_encoder_param_count_and_posterior_semantics():
+    """Encoder 34,163,592 + quant_conv 72 parameters (with the decoder's 49,490,199: the published 83,653,863); the
+    posterior clamps the log-variance to [-30, 20] and `encode` is (mean + std * noise) * scaling_factor."""
+    import dataclasses
+    from cfgpp_b200 import vae as V
+    from oracle import vae as OV
+    for cfg in (V.sdxl_vae_config(), V.sd15_vae_config()):
+        assert V.num_vae_encoder_params(cfg) == 34_163_592 + 72
+        assert V.num_vae_encoder_params(cfg) + V.num_vae_decoder_params(cfg) == 83_653_863
+        with torch.device("meta"):
+            m = OV.AutoencoderKLEncoder(OV.VAEConfig(**{f.name: getattr(cfg, f.name) for f in dataclasses.fields(OV.VAEConfig)}))
+        assert OV.count_params(m) == V.num_vae_encoder_params(cfg) and OV.count_params(m.encoder) == 34_163_592
+        assert set(m.state_dict().keys()) == {k for k, _, _ in V.vae_encoder_param_specs(cfg)}
+    cfg = V.tiny_vae_config()
+    sd = V.synthetic_vae_state_dict(cfg, seed=3, with_encoder=True)
+    assert {k for k in sd if k.startswith(("decoder.", "post_quant_conv."))} == set(V.synthetic_vae_state_dict(cfg, seed=3))
+    ocfg = OV.VAEConfig(**{f.name: getattr(cfg, f.name) for f in dataclasses.fields(OV.VAEConfig)})
+    m = OV.build_vae_encoder(ocfg, {k: v for k, v in sd.items() if k.startswith(("encoder.", "quant_conv."))})
+    x = torch.rand(1, 3, 64, 64) * 2 - 1
+    mean, std = m(x)
+    noise = torch.randn_like(mean)
+    assert torch.allclose(OV.encode(m, x, noise), (mean + std * noise) * cfg.scaling_factor)
+    m.quant_conv.bias.data[4:] = 100.0      # log-variance far above the clamp
+    _, std_hi = m(x)
+    assert torch.allclose(std_hi, torch.full_like(std_hi, float(torch.exp(torch.tensor(10.0)))))
+    m.quant_conv.bias.data[4:] = -100.0
+    _, std_lo = m(x)
+    assert torch.allclose(std_lo, torch.full_like(std_lo, float(torch.exp(torch.tensor(-15.0)))))
