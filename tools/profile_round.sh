@@ -24,5 +24,5 @@ full attn attn_kernel 30 2         # self-attention, N = 1024 x 20 heads
 full xattn xattn_kernel 30 2       # cross-attention, 77 keys
 full gn gn_ 0 4                    # gn_stats + gn_apply at 128x128x320 (x2)
 full convio conv_ 0 2              # conv_in_kernel, conv_out_step_kernel (the fused CFG++ / DDIM epilogue)
-full small "small_linear|sincos|select_step|im2col|upsample" 0 8
+full small "small_linear|sincos|select_step|upsample" 0 8
 ls -la gpurun_out | head -40
