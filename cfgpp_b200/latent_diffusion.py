@@ -5,8 +5,9 @@ base (:54-241: `alpha`, `get_text_embed`, `encode`, `decode`, `predict_noise`, `
 `ddim_cfg++` (:621-679) and `ddim_inversion_cfg++` (:882-957). Same names, argument meaning and errors; the UNet
 forward, CFG++ mix and DDIM update run in hand-written sm_100a CUDA behind include/cfgpp_b200.h.
 SURVEY §8 f1 (the rest of the CFG++ `--method` surface): `ddim_edit_cfg++` (:959-1010) on the same fused step modes;
-`euler_cfg++` (:682-724), `euler_a_cfg++` (:727-768), `dpm++_2s_a_cfg++` (:771-827), `dpm++_2m_cfg++` (:830-879) with
-the native UNet behind `predict_noise` and their few elementwise update ops in torch (kdiffusion.py).
+`euler_cfg++` (:682-724), `euler_a_cfg++` (:727-768), `dpm++_2s_a_cfg++` (:771-827), `dpm++_2m_cfg++` (:830-879) as
+fused VE-cast trajectories (kdiffusion.py: the ancestral ones with their noise drawn up front); the op-by-op torch
+form over `predict_noise` runs when a callback is installed.
 
 dtype note (reference promotion rules): `ddim_cfg++` keeps an fp32 latent state (zT is a fp32
 `torch.randn`); `ddim_inversion_cfg++` starts from the fp16 VAE latent, so both its inversion loop and the following

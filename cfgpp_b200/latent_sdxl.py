@@ -12,8 +12,9 @@ no host synchronisation; with a callback the un-fused seam (`predict_noise` + `a
 
 Registered here: ddim_cfg++, ddim_cfg++_lightning, dpm++_2m_cfgpp (the solvers of SURVEY.md §8a) and, from §8 f1,
 dpm++_2m_cfgpp_lightning (:932-952), ddim_edit_cfg++ (:954-1025, both loops on the fused step modes), euler_cfg++ and
-euler_cfg++_lightning (:757-836: native UNet behind `predict_noise`, the Euler update in torch — kdiffusion.py).
-The VAE decode runs on the native decoder (vae.py); text encoders stay pluggable (conditioning.py).
+euler_cfg++_lightning (:757-836: fused VE-cast trajectories, kdiffusion.py; the op-by-op torch form only with a callback).
+The VAE (decode and encode, vae.py) and the two CLIP text towers (text_encoder.py, §8 f3) run on the
+native backend too; `text_encoders=` / `vae=` accept replacements.
 """
 from __future__ import annotations
 
