@@ -10,6 +10,7 @@ from types import SimpleNamespace
 
 import torch
 
+from cfgpp_b200.checkpoints import solver_components
 from cfgpp_b200.latent_diffusion import get_solver
 from cfgpp_b200.latent_sdxl import get_solver as get_solver_sdxl
 from cfgpp_b200.utils.log_util import create_workdir, set_seed
@@ -42,6 +43,9 @@ def main():
     parser.add_argument("--model", type=str, default='sd15', choices=["sd15", "sd20", "sdxl"])
     parser.add_argument("--NFE", type=int, default=10)
     parser.add_argument("--seed", type=int, default=42)
+    parser.add_argument("--ckpt_dir", type=Path, default=None,
+                        help="diffusers-format pipeline directory (unet/, vae/, text_encoder[_2]/, tokenizer[_2]/); "
+                             "default: seeded synthetic weights (nothing can be downloaded here)")
     args = parser.parse_args()
 
     set_seed(args.seed)
@@ -51,11 +55,13 @@ def main():
     prompts = [args.null_prompt, args.prompt, args.tgt_prompt if args.tgt_prompt is not None else args.prompt]
 
     if args.model == "sdxl":
-        solver = get_solver_sdxl(args.method, solver_config=solver_config, device=args.device)
+        extra = solver_components(args.ckpt_dir, "sdxl", args.device) if args.ckpt_dir else {}
+        solver = get_solver_sdxl(args.method, solver_config=solver_config, device=args.device, **extra)
         result = solver.sample(prompt1=prompts, prompt2=prompts, src_img=img, cfg_guidance=args.cfg_guidance,
                                target_size=(args.img_size, args.img_size))
     else:
-        solver = get_solver(args.method, solver_config=solver_config, device=args.device)
+        extra = solver_components(args.ckpt_dir, "sd15", args.device) if args.ckpt_dir else {}
+        solver = get_solver(args.method, solver_config=solver_config, device=args.device, **extra)
         result = solver.sample(prompt=prompts, src_img=img, cfg_guidance=args.cfg_guidance, callback_fn=None)
 
     out = args.workdir.joinpath('result/reconstruct.pt')

@@ -8,6 +8,7 @@ from types import SimpleNamespace
 
 import torch
 
+from cfgpp_b200.checkpoints import solver_components
 from cfgpp_b200.latent_diffusion import get_solver
 from cfgpp_b200.latent_sdxl import get_solver as get_solver_sdxl
 from cfgpp_b200.utils.log_util import create_workdir, set_seed
@@ -24,6 +25,9 @@ def main():
     parser.add_argument("--model", type=str, default='sd15', choices=["sd15", "sd20", "sdxl", "sdxl_lightning"])
     parser.add_argument("--NFE", type=int, default=50)
     parser.add_argument("--seed", type=int, default=42)
+    parser.add_argument("--ckpt_dir", type=Path, default=None,
+                        help="diffusers-format pipeline directory (unet/, vae/, text_encoder[_2]/, tokenizer[_2]/); "
+                             "default: seeded synthetic weights (nothing can be downloaded here)")
     args = parser.parse_args()
 
     set_seed(args.seed)
@@ -32,11 +36,13 @@ def main():
     callback = None
 
     if args.model in ("sdxl", "sdxl_lightning"):
-        solver = get_solver_sdxl(args.method, solver_config=solver_config, device=args.device)
+        extra = solver_components(args.ckpt_dir, "sdxl", args.device) if args.ckpt_dir else {}
+        solver = get_solver_sdxl(args.method, solver_config=solver_config, device=args.device, **extra)
         result = solver.sample(prompt1=[args.null_prompt, args.prompt], prompt2=[args.null_prompt, args.prompt],
                                cfg_guidance=args.cfg_guidance, target_size=(1024, 1024), callback_fn=callback)
     else:
-        solver = get_solver(args.method, solver_config=solver_config, device=args.device)
+        extra = solver_components(args.ckpt_dir, "sd15", args.device) if args.ckpt_dir else {}
+        solver = get_solver(args.method, solver_config=solver_config, device=args.device, **extra)
         result = solver.sample(prompt=[args.null_prompt, args.prompt], cfg_guidance=args.cfg_guidance,
                                callback_fn=callback)
 

@@ -39,6 +39,9 @@ def main():
     parser.add_argument("--model", type=str, default='sd15', choices=["sd15", "sd20", "sdxl", "sdxl_lightning"])
     parser.add_argument("--NFE", type=int, default=50)
     parser.add_argument("--seed", type=int, default=42)
+    parser.add_argument("--ckpt_dir", type=Path, default=None,
+                        help="diffusers-format pipeline directory (unet/, vae/, text_encoder[_2]/, tokenizer[_2]/); "
+                             "default: seeded synthetic weights (nothing can be downloaded here)")
     args = parser.parse_args()
 
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
@@ -59,7 +62,10 @@ def main():
     cfg = sdxl_config() if sdxl else sd15_config()
 
     kw = {}
-    if world > 1:  # one bucketed NCCL broadcast of rank 0's weights; afterwards the ranks never talk again
+    if args.ckpt_dir:  # every rank reads the pipeline directory itself (UNet, VAE, text towers, tokenizers)
+        from cfgpp_b200.checkpoints import solver_components
+        kw = solver_components(args.ckpt_dir, "sdxl" if sdxl else "sd15", device)
+    elif world > 1:  # one bucketed NCCL broadcast of rank 0's weights; afterwards the ranks never talk again
         sd = Wt.synthetic_state_dict(cfg, seed=1234, device=device) if rank == 0 else None
         kw["state_dict"] = D.broadcast_state_dict(sd, Wt.unet_param_specs(cfg), device, src=0)
     solver = (get_solver_sdxl if sdxl else get_solver)(args.method, solver_config=solver_config, device=device, **kw)

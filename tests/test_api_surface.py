@@ -113,3 +113,25 @@ def test_checkpoint_resolution_round_trip(tmp_path):
     with pytest.warns(UserWarning, match="no checkpoint"):
         other = resolve_state_dict("stabilityai/stable-diffusion-xl-base-1.0", cfg, "cpu")
     assert set(other) == set(sd)
+
+
+def test_pipeline_directory_resolver(tmp_path):
+    """cfgpp_b200.checkpoints: the diffusers pipeline layout the reference's from_pretrained reads (latent_sdxl.py:41-49)."""
+    from cfgpp_b200.checkpoints import find_pipeline_files
+    import pytest as _pt
+    with _pt.raises(FileNotFoundError) as e:
+        find_pipeline_files(tmp_path, "sdxl")
+    assert "text_encoder_2" in str(e.value) and "tokenizer_2" in str(e.value) and "unet" in str(e.value)
+    for d, name in (("unet", "diffusion_pytorch_model.fp16.safetensors"), ("vae", "diffusion_pytorch_model.safetensors"),
+                    ("text_encoder", "model.safetensors"), ("text_encoder_2", "model.fp16.safetensors")):
+        (tmp_path / d).mkdir()
+        (tmp_path / d / name).write_bytes(b"")
+    for t in ("tokenizer", "tokenizer_2"):
+        (tmp_path / t).mkdir()
+        (tmp_path / t / "vocab.json").write_text("{}")
+        (tmp_path / t / "merges.txt").write_text("#version: 0.2\n")
+    f = find_pipeline_files(tmp_path, "sdxl")
+    assert f["unet"].name.endswith(".fp16.safetensors") and f["text_encoder_2"].parent.name == "text_encoder_2"
+    assert set(find_pipeline_files(tmp_path, "sd15")) == {"unet", "vae", "text_encoder", "tokenizer/vocab.json", "tokenizer/merges.txt"}
+    with _pt.raises(ValueError):
+        find_pipeline_files(tmp_path, "sd3")
