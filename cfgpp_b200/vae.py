@@ -15,7 +15,7 @@ from __future__ import annotations
 import ctypes
 import math
 import warnings
-from ctypes import POINTER, byref, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
+from ctypes import byref, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
 from dataclasses import dataclass
 from typing import Dict, List, Tuple
 

@@ -16,7 +16,6 @@ Only tests/, __graft_entry__.smoke() and bench.py may import this package.
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass
 from typing import List, Optional, Tuple
 
